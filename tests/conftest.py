@@ -1,0 +1,27 @@
+"""pytest configuration: registers the `gpu` marker and locates the libraries.
+
+-m "not gpu": oracle vs golden vectors / compiled reference, host logic (ier
+codes, wsave tables), C-ABI symbol exports, gloo sharding test.
+-m gpu: parity tests proper; they call the CUDA library through its C ABI.
+"""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    # build the checker (oracle) and the product library once per session
+    if os.environ.get("CFB200_SKIP_BUILD") != "1":  # developer shortcut; the driver never sets it
+        import __graft_entry__ as ge
+        ge.build()
+    yield
