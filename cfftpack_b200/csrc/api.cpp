@@ -1,0 +1,368 @@
+/*
+ * api.cpp -- the FFTPACK 5.1 entry points (include/cfftpack_b200.h) over the CUDA drivers.
+ *
+ * Each routine performs the argument checks of its reference twin with the reference's own expressions, so
+ * that ier agrees value for value (cfft1f_ fftpack.c:2218-2228, cfftmf_ :2577-2590, cfft2f_ :2392-2405,
+ * rfft1f_ :13053-13065, rfftmf_ :14057-14069, cost1f_ :6071-6084, costmf_ :6510-6530, sint1f_ :14640-14651,
+ * sintmf_ :15025-15045, cosq1f_ :5480-5485, cosqmf_ :5870-5890), then hands DEVICE pointers to dispatch.cu.
+ * Host arrays are staged through HBM here.  Nothing in this file computes a transform on the CPU.
+ */
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "../../include/cfftpack_b200.h"
+#include "internal.h"
+#include "plan.h"
+
+namespace cfb {
+
+/* ---------------- runtime plumbing ---------------- */
+static thread_local char t_err[512] = "";
+static thread_local cudaStream_t t_stream = 0;
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+const char *last_error() { return t_err; }
+bool cuda_ok(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return true;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return false;
+}
+cudaStream_t current_stream() { return t_stream; }
+void set_current_stream(cudaStream_t s) { t_stream = s; }
+void count_launch(unsigned long long k) { g_launches += k; }
+unsigned long long launch_count() { return g_launches.load(); }
+
+bool device_ready() {
+  static std::once_flag once;
+  static bool ok = false;
+  static char why[256] = "";
+  std::call_once(once, [] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+      snprintf(why, sizeof(why), "no CUDA device (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+      fprintf(stderr,
+              "libcfftpack_b200: FATAL: %s. This library has no CPU path; transforms will fail with ier = -1.\n", why);
+      return;
+    }
+    ok = true;
+  });
+  if (!ok) set_error("%s", why);
+  return ok;
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    cudaDeviceProp p;
+    int d = 0;
+    cudaGetDevice(&d);
+    if (cudaGetDeviceProperties(&p, d) == cudaSuccess) sms = p.multiProcessorCount;
+    else sms = 148;
+  }
+  return sms;
+}
+
+struct Scratch {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+struct ScratchSet {
+  Scratch s[4];
+  ~ScratchSet() {
+    for (auto &x : s)
+      if (x.p) cudaFree(x.p);
+  }
+};
+static thread_local ScratchSet t_scr;
+void *scratch_get(int slot, size_t bytes) {
+  Scratch &s = t_scr.s[slot];
+  if (s.cap >= bytes && s.p) return s.p;
+  if (s.p) {
+    cudaStreamSynchronize(t_stream);
+    cudaFree(s.p);
+    s.p = nullptr;
+    s.cap = 0;
+  }
+  size_t cap = bytes + bytes / 8 + 4096;
+  if (!cuda_ok(cudaMalloc(&s.p, cap), "cudaMalloc(scratch)")) {
+    s.p = nullptr;
+    return nullptr;
+  }
+  s.cap = cap;
+  return s.p;
+}
+void scratch_release_all() {
+  for (auto &x : t_scr.s) {
+    if (x.p) cudaFree(x.p);
+    x.p = nullptr;
+    x.cap = 0;
+  }
+}
+
+/* a caller array, resolved to device memory */
+struct DeviceView {
+  void *dev = nullptr;
+  void *host = nullptr;
+  size_t bytes = 0;
+  bool staged = false;
+};
+static bool view_open(void *user, size_t bytes, DeviceView &v) {
+  if (!device_ready()) return false;
+  cudaPointerAttributes at;
+  memset(&at, 0, sizeof(at));
+  cudaError_t e = cudaPointerGetAttributes(&at, user);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    at.type = cudaMemoryTypeUnregistered;
+  }
+  v.bytes = bytes;
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) {
+    v.dev = user;
+    return true;
+  }
+  v.host = user;
+  v.staged = true;
+  v.dev = scratch_get(1, bytes);
+  if (!v.dev) return false;
+  return cuda_ok(cudaMemcpyAsync(v.dev, user, bytes, cudaMemcpyHostToDevice, t_stream), "cudaMemcpyAsync(H2D)");
+}
+static bool view_close(DeviceView &v, bool ok) {
+  if (!v.staged) return ok;
+  if (ok) ok = cuda_ok(cudaMemcpyAsync(v.host, v.dev, v.bytes, cudaMemcpyDeviceToHost, t_stream), "cudaMemcpyAsync(D2H)");
+  bool s = cuda_ok(cudaStreamSynchronize(t_stream), "cudaStreamSynchronize");
+  return ok && s;
+}
+
+static inline long long span1(int n, int inc) { return (long long)inc * (n - 1) + 1; }
+static inline long long spanm(int lot, int jump, int n, int inc) {
+  return (long long)(lot - 1) * jump + (long long)inc * (n - 1) + 1;
+}
+
+/* ---------------- complex ---------------- */
+static int complex_init(int *n, double *wsave, int *lensav, int *ier) {
+  *ier = 0;
+  if (*lensav < 2 * *n + log2_floor_ref(*n) + 4) {
+    *ier = 2;
+    return 0;
+  }
+  if (*n == 1) return 0;
+  wsave_init_complex(*n, wsave);
+  return 0;
+}
+
+static int complex_1d(int *n, int *inc, void *c, int *lenc, int *lensav, int *lenwrk, int *ier, int dir) {
+  *ier = 0;
+  if (*lenc < span1(*n, *inc)) *ier = 1;
+  else if (*lensav < 2 * *n + log2_floor_ref(*n) + 4) *ier = 2;
+  else if (*lenwrk < 2 * *n) *ier = 3;
+  if (*ier || *n == 1) return 0;
+  DeviceView v;
+  bool ok = view_open(c, (size_t)span1(*n, *inc) * 16, v);
+  if (ok) ok = run_c2c(*n, 1, *inc, (long long)*inc * *n, dir, v.dev);
+  ok = view_close(v, ok);
+  if (!ok) *ier = -1;
+  return 0;
+}
+
+static int complex_multi(int *lot, int *jump, int *n, int *inc, void *c, int *lenc, int *lensav, int *lenwrk, int *ier,
+                         int dir) {
+  *ier = 0;
+  if (*lenc < spanm(*lot, *jump, *n, *inc)) *ier = 1;
+  else if (*lensav < 2 * *n + log2_floor_ref(*n) + 4) *ier = 2;
+  else if ((long long)*lenwrk < 2LL * *lot * *n) *ier = 3;
+  else if (!strides_consistent(*inc, *jump, *n, *lot)) *ier = 4;
+  if (*ier || *n == 1) return 0;
+  DeviceView v;
+  bool ok = view_open(c, (size_t)spanm(*lot, *jump, *n, *inc) * 16, v);
+  if (ok) ok = run_c2c(*n, *lot, *inc, *jump, dir, v.dev);
+  ok = view_close(v, ok);
+  if (!ok) *ier = -1;
+  return 0;
+}
+
+static int complex_2d(int *ldim, int *l, int *m, void *c, int *lensav, int *lenwrk, int *ier, int dir) {
+  *ier = 0;
+  if (*l > *ldim) *ier = 5;
+  else if (*lensav < 2 * *l + log2_floor_ref(*l) + 2 * *m + log2_floor_ref(*m) + 8) *ier = 2;
+  else if ((long long)*lenwrk < 2LL * *l * *m) *ier = 3;
+  if (*ier) return 0;
+  DeviceView v;
+  bool ok = view_open(c, ((size_t)*ldim * (*m - 1) + *l) * 16, v);
+  if (ok) ok = run_c2c_2d(*ldim, *l, *m, dir, v.dev);
+  ok = view_close(v, ok);
+  if (!ok) *ier = -1;
+  return 0;
+}
+
+/* ---------------- real families ---------------- */
+static int fam_lensav(int kind, int n) {
+  switch (kind) {
+    case K_RFFT: return n + log2_floor_ref(n) + 4;
+    case K_SINT: return n / 2 + n + log2_floor_ref(n) + 4;
+    default: return 2 * n + log2_floor_ref(n) + 4;
+  }
+}
+static long long fam_lenwrk(int kind, int n, long long lot, bool multi) {
+  switch (kind) {
+    case K_RFFT: return multi ? lot * n : n;
+    case K_COST: return multi ? lot * (n + 1) : n - 1;
+    case K_SINT: return multi ? lot * (2LL * n + 4) : 2 * n + 2;
+    default: return multi ? lot * n : n;
+  }
+}
+
+static int real_init(int kind, int *n, double *wsave, int *lensav, int *ier) {
+  *ier = 0;
+  if (*lensav < fam_lensav(kind, *n)) {
+    *ier = 2;
+    return 0;
+  }
+  switch (kind) {
+    case K_RFFT:
+      if (*n > 1) wsave_init_real(*n, wsave);
+      break;
+    case K_COST: wsave_init_cost(*n, wsave); break;
+    case K_SINT: wsave_init_sint(*n, wsave); break;
+    default: wsave_init_cosq(*n, wsave); break;
+  }
+  return 0;
+}
+
+static int real_1d(int kind, int *n, int *inc, double *x, int *lenx, int *lensav, int *lenwrk, int *ier, int dir) {
+  *ier = 0;
+  if (*lenx < span1(*n, *inc)) *ier = 1;
+  else if (*lensav < fam_lensav(kind, *n)) *ier = 2;
+  else if (*lenwrk < fam_lenwrk(kind, *n, 1, false)) *ier = 3;
+  if (*ier || *n == 1) return 0;
+  DeviceView v;
+  bool ok = view_open(x, (size_t)span1(*n, *inc) * 8, v);
+  if (ok) ok = run_real(kind, *n, 1, *inc, (long long)*inc * *n, dir, (double *)v.dev);
+  ok = view_close(v, ok);
+  if (!ok) *ier = -1;
+  return 0;
+}
+
+static int real_multi(int kind, int *lot, int *jump, int *n, int *inc, double *x, int *lenx, int *lensav, int *lenwrk,
+                      int *ier, int dir) {
+  *ier = 0;
+  if (*lenx < spanm(*lot, *jump, *n, *inc)) *ier = 1;
+  else if (*lensav < fam_lensav(kind, *n)) *ier = 2;
+  else if ((long long)*lenwrk < fam_lenwrk(kind, *n, *lot, true)) *ier = 3;
+  else if (!strides_consistent(*inc, *jump, *n, *lot)) *ier = 4;
+  if (*ier || *n == 1) return 0;
+  DeviceView v;
+  bool ok = view_open(x, (size_t)spanm(*lot, *jump, *n, *inc) * 8, v);
+  if (ok) ok = run_real(kind, *n, *lot, *inc, *jump, dir, (double *)v.dev);
+  ok = view_close(v, ok);
+  if (!ok) *ier = -1;
+  return 0;
+}
+
+}  // namespace cfb
+
+using namespace cfb;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int cfft1i_(int *n, double *wsave, int *lensav, int *ier) { return complex_init(n, wsave, lensav, ier); }
+int cfftmi_(int *n, double *wsave, int *lensav, int *ier) { return complex_init(n, wsave, lensav, ier); }
+int cfft1f_(int *n, int *inc, fft_complex_t *c, int *lenc, double *, int *lensav, double *, int *lenwrk, int *ier) {
+  return complex_1d(n, inc, c, lenc, lensav, lenwrk, ier, -1);
+}
+int cfft1b_(int *n, int *inc, fft_complex_t *c, int *lenc, double *, int *lensav, double *, int *lenwrk, int *ier) {
+  return complex_1d(n, inc, c, lenc, lensav, lenwrk, ier, +1);
+}
+int cfftmf_(int *lot, int *jump, int *n, int *inc, fft_complex_t *c, int *lenc, double *, int *lensav, double *,
+            int *lenwrk, int *ier) {
+  return complex_multi(lot, jump, n, inc, c, lenc, lensav, lenwrk, ier, -1);
+}
+int cfftmb_(int *lot, int *jump, int *n, int *inc, fft_complex_t *c, int *lenc, double *, int *lensav, double *,
+            int *lenwrk, int *ier) {
+  return complex_multi(lot, jump, n, inc, c, lenc, lensav, lenwrk, ier, +1);
+}
+
+int cfft2i_(int *l, int *m, double *wsave, int *lensav, int *ier) {
+  *ier = 0;
+  if (*lensav < 2 * *l + log2_floor_ref(*l) + 2 * *m + log2_floor_ref(*m) + 8) {
+    *ier = 2;
+    return 0;
+  }
+  int ier1 = 0, ls = 2 * *l + log2_floor_ref(*l) + 4;
+  complex_init(l, wsave, &ls, &ier1);
+  if (ier1) {
+    *ier = 20;
+    return 0;
+  }
+  ls = 2 * *m + log2_floor_ref(*m) + 4;
+  complex_init(m, wsave + 2 * *l + log2_floor_ref(*l) + 2, &ls, &ier1);
+  if (ier1) *ier = 20;
+  return 0;
+}
+int cfft2f_(int *ldim, int *l, int *m, fft_complex_t *c, double *, int *lensav, double *, int *lenwrk, int *ier) {
+  return complex_2d(ldim, l, m, c, lensav, lenwrk, ier, -1);
+}
+int cfft2b_(int *ldim, int *l, int *m, fft_complex_t *c, double *, int *lensav, double *, int *lenwrk, int *ier) {
+  return complex_2d(ldim, l, m, c, lensav, lenwrk, ier, +1);
+}
+
+#define CFB_DEF_REAL(name, K)                                                                                          \
+  int name##1i_(int *n, double *wsave, int *lensav, int *ier) { return real_init(K, n, wsave, lensav, ier); }          \
+  int name##mi_(int *n, double *wsave, int *lensav, int *ier) { return real_init(K, n, wsave, lensav, ier); }          \
+  int name##1f_(int *n, int *inc, double *x, int *lenx, double *, int *lensav, double *, int *lenwrk, int *ier) {      \
+    return real_1d(K, n, inc, x, lenx, lensav, lenwrk, ier, -1);                                                       \
+  }                                                                                                                    \
+  int name##1b_(int *n, int *inc, double *x, int *lenx, double *, int *lensav, double *, int *lenwrk, int *ier) {      \
+    return real_1d(K, n, inc, x, lenx, lensav, lenwrk, ier, +1);                                                       \
+  }                                                                                                                    \
+  int name##mf_(int *lot, int *jump, int *n, int *inc, double *x, int *lenx, double *, int *lensav, double *,          \
+                int *lenwrk, int *ier) {                                                                               \
+    return real_multi(K, lot, jump, n, inc, x, lenx, lensav, lenwrk, ier, -1);                                         \
+  }                                                                                                                    \
+  int name##mb_(int *lot, int *jump, int *n, int *inc, double *x, int *lenx, double *, int *lensav, double *,          \
+                int *lenwrk, int *ier) {                                                                               \
+    return real_multi(K, lot, jump, n, inc, x, lenx, lensav, lenwrk, ier, +1);                                         \
+  }
+CFB_DEF_REAL(rfft, K_RFFT)
+CFB_DEF_REAL(cost, K_COST)
+CFB_DEF_REAL(sint, K_SINT)
+CFB_DEF_REAL(cosq, K_COSQ)
+CFB_DEF_REAL(sinq, K_SINQ)
+
+int cfb200_set_stream(void *s) {
+  set_current_stream((cudaStream_t)s);
+  return 0;
+}
+int cfb200_synchronize(void) {
+  if (!device_ready()) return -1;
+  return cuda_ok(cudaStreamSynchronize(current_stream()), "cudaStreamSynchronize") ? 0 : -1;
+}
+unsigned long long cfb200_launch_count(void) { return launch_count(); }
+const char *cfb200_last_error(void) { return last_error(); }
+void cfb200_release(void) {
+  release_plans();
+  scratch_release_all();
+}
+const char *cfb200_version(void) {
+#ifdef CFB_SIM
+  return "cfftpack_b200 0.1 SIM (CPU thread emulator, tests only)";
+#else
+  return "cfftpack_b200 0.1 sm_100a";
+#endif
+}
+int cfb200_max_onchip_complex(void) { return engine_max_c2c(); }
+int cfb200_max_onchip_real(void) { return engine_max_real(); }
+}
+#pragma GCC visibility pop

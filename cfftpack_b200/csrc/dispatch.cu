@@ -1,0 +1,211 @@
+/*
+ * dispatch.cu -- chooses a kernel and a launch geometry for each transform request.
+ *
+ *   contiguous power-of-two batches (cfftmf_/rfftmf_ headline shape)  -> pow2.cuh register kernels
+ *   everything else that fits one CTA                                   -> engine.cuh
+ *   long complex transforms                                             -> four-step: two engine sweeps
+ *                                                                          through a device scratch array
+ * There is no CPU path: a failure to launch is reported to the caller through ier.
+ */
+#include <stdio.h>
+
+#include <mutex>
+
+#include "engine.cuh"
+#include "internal.h"
+#include "plan.h"
+#include "pow2.cuh"
+
+namespace cfb {
+
+static const size_t SMEM_MAX = 227 * 1024;      // opt-in limit per CTA on sm_100
+static const size_t SMEM_TARGET = 72 * 1024;    // aim: three CTAs per SM for the streaming kernels
+
+int engine_max_c2c() { return (int)((SMEM_MAX - 1024) / 32) - 2; }
+int engine_max_real() { return (int)((SMEM_MAX - 2048) / 48) - 4; }
+
+static bool engine_attr_once() {
+  static std::once_flag once;
+  static bool ok = true;
+  std::call_once(once, [] {
+    ok = cuda_ok(cudaFuncSetAttribute(engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
+                 "cudaFuncSetAttribute(engine_kernel)");
+  });
+  return ok;
+}
+
+static void fill_passes(EngineParams &P, const CorePlan *cp) {
+  P.M = cp->M;
+  P.nf = cp->nf;
+  for (int i = 0; i < cp->nf; ++i) P.pass[i] = cp->pass[i];
+  P.tw = cp->d_tw;
+}
+
+static Addr make_addr(long long inc, long long jump_lo, long long jump_hi, long long nlo) {
+  Addr a;
+  a.inc = inc;
+  a.jump_lo = jump_lo;
+  a.jump_hi = jump_hi;
+  a.nlo = (int)nlo;
+  long long ai = inc < 0 ? -inc : inc, aj = jump_lo < 0 ? -jump_lo : jump_lo;
+  a.lanes_t = (aj < ai) ? 1 : 0;
+  return a;
+}
+
+/* one engine launch; P has kind/dir/n/addresses/plan filled in */
+static bool launch_engine(EngineParams &P) {
+  if (!engine_attr_once()) return false;
+  const bool real = P.kind != K_C2C;
+  P.ldz = P.M | 1;
+  P.ldx = (P.n + 1) | 1;
+  const size_t per = real ? (size_t)P.ldz * 32 + (size_t)P.ldx * 16 + 16 : (size_t)P.ldz * 32;
+  const long long units = real ? (P.lot + 1) / 2 : P.lot;
+  if (per > SMEM_MAX) {
+    set_error("length %d does not fit one CTA (%zu bytes)", P.n, per);
+    return false;
+  }
+  long long T = (long long)(SMEM_TARGET / per);
+  const bool strided = P.ain.lanes_t || P.aout.lanes_t;
+  // batch-contiguous layouts want at least 8 sequences side by side (128-byte runs of 16-byte elements)
+  const long long want = strided ? (real ? 4 : 8) : 1;
+  if (T < want) T = (long long)(SMEM_MAX / per) < want ? (long long)(SMEM_MAX / per) : want;
+  if (T < 1) T = 1;
+  if (T > 32) T = 32;
+  if (T > units) T = units;
+  // two-level batches: keep a tile inside one group when that costs nothing
+  P.T = (int)T;
+  const size_t smem = per * (size_t)T;
+  const long long grid = (units + T - 1) / T;
+  if (grid > 2147483647LL) {
+    set_error("batch too large");
+    return false;
+  }
+  CFB_LAUNCH(engine_kernel, (unsigned)grid, CFB_ENGINE_THREADS, smem, current_stream(), P);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "engine_kernel launch");
+}
+
+/* split n = n1 * n2 with both factors as close to sqrt(n) as the limit allows; 0 if impossible */
+static int four_step_split(int n, int limit) {
+  int best = 0;
+  for (int d = 1; (long long)d * d <= n; ++d)
+    if (n % d == 0 && n / d <= limit) {
+      best = d;  // largest d <= sqrt(n); n/d shrinks as d grows
+    }
+  return best;  // n1 = best (<= n2 = n / best)
+}
+
+bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void *c) {
+  if (n <= 1 || lot <= 0) return true;
+  const int aligned = (((uintptr_t)c) & 15) == 0;
+  if (pow2_c2c_supported(n, inc, jump, aligned)) return pow2_c2c_launch(n, lot, jump, dir, (cpx *)c);
+  EngineParams P;
+  memset(&P, 0, sizeof(P));
+  P.kind = K_C2C;
+  P.dir = dir;
+  P.n = n;
+  P.aligned16 = aligned;
+  if (n <= engine_max_c2c()) {
+    const CorePlan *cp = get_core_plan(n);
+    if (!cp) return false;
+    fill_passes(P, cp);
+    P.lot = lot;
+    P.ain = P.aout = make_addr(inc, jump, 0, 1LL << 30);
+    P.in = c;
+    P.out = c;
+    P.scale = dir < 0 ? 1.0 / (double)n : 1.0;
+    return launch_engine(P);
+  }
+  /* four-step: x[j1*n2 + j2] -> (FFT over j1) * W_n^{j2 k1} -> scratch[k1*n2 + j2] -> (FFT over j2) -> X[k1 + n1 k2] */
+  const int n1 = four_step_split(n, engine_max_c2c());
+  if (n1 <= 1) {
+    set_error("length %d has a prime factor too large for the four-step path", n);
+    return false;
+  }
+  const int n2 = n / n1;
+  if (lot * (long long)n2 > 2147483647LL * 16 || lot * (long long)n1 > 2147483647LL * 16) {
+    set_error("batch too large");
+    return false;
+  }
+  const CorePlan *p1 = get_core_plan(n1), *p2 = get_core_plan(n2);
+  const RootPlan *rp = get_root_plan(n);
+  if (!p1 || !p2 || !rp) return false;
+  cpx *scr = (cpx *)scratch_get(0, (size_t)lot * n * sizeof(cpx));
+  if (!scr) return false;
+  // step 1
+  fill_passes(P, p1);
+  P.n = n1;
+  P.lot = lot * n2;
+  P.ain = make_addr((long long)n2 * inc, inc, jump, n2);
+  P.aout = make_addr(n2, 1, n, n2);
+  P.in = c;
+  P.out = scr;
+  P.scale = 1.0;
+  P.fs_tw = rp->d_w;
+  P.fs_n = n;
+  if (!launch_engine(P)) return false;
+  // step 2
+  fill_passes(P, p2);
+  P.n = n2;
+  P.lot = lot * n1;
+  P.ain = make_addr(1, n2, n, n1);
+  P.aout = make_addr((long long)n1 * inc, inc, jump, n1);
+  P.in = scr;
+  P.out = c;
+  P.scale = dir < 0 ? 1.0 / (double)n : 1.0;
+  P.fs_tw = nullptr;
+  P.fs_n = 0;
+  return launch_engine(P);
+}
+
+bool run_c2c_2d(int ldim, int l, int m, int dir, void *c) {
+  // cfft2f_ order (fftpack.c:2408-2426): lines along the second index first, then along the first
+  if (!run_c2c(m, l, ldim, 1, dir, c)) return false;
+  return run_c2c(l, m, 1, ldim, dir, c);
+}
+
+bool run_real(int kind, int n, long long lot, long long inc, long long jump, int dir, double *x) {
+  if (n <= 1 || lot <= 0) return true;
+  const bool tiny = (kind == K_COST && n <= 3) || (kind != K_RFFT && n == 2);
+  if (tiny) {
+    TinyParams tp;
+    tp.kind = kind;
+    tp.dir = dir;
+    tp.n = n;
+    tp.lot = lot;
+    tp.a = make_addr(inc, jump, 0, 1LL << 30);
+    tp.x = x;
+    long long grid = (lot + 127) / 128;
+    CFB_LAUNCH(tiny_kernel, (unsigned)grid, 128, 0, current_stream(), tp);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "tiny_kernel launch");
+  }
+  if (kind == K_RFFT && pow2_r2c_supported(n, inc, jump, (((uintptr_t)x) & 15) == 0))
+    return pow2_r2c_launch(n, lot, jump, dir, x);
+  const int M = kind == K_COST ? n - 1 : kind == K_SINT ? n + 1 : n;
+  if (M > engine_max_real()) {
+    set_error("real-family length %d exceeds the single-CTA limit %d", n, engine_max_real());
+    return false;
+  }
+  EngineParams P;
+  memset(&P, 0, sizeof(P));
+  P.kind = kind;
+  P.dir = dir;
+  P.n = n;
+  const CorePlan *cp = get_core_plan(M);
+  if (!cp) return false;
+  fill_passes(P, cp);
+  if (kind != K_RFFT) {
+    const TrigPlan *tp = get_trig_plan(kind == K_SINQ ? K_COSQ : kind, n);
+    if (!tp) return false;
+    P.trig = tp->d_trig;
+  }
+  P.lot = lot;
+  P.ain = P.aout = make_addr(inc, jump, 0, 1LL << 30);
+  P.in = x;
+  P.out = x;
+  P.scale = 1.0;
+  return launch_engine(P);
+}
+
+}  // namespace cfb

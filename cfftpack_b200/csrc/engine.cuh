@@ -1,0 +1,574 @@
+/*
+ * engine.cuh -- the general shared-memory transform engine (any length, any stride).
+ *
+ * One CTA keeps T complex sequences of length M in shared memory, runs every radix pass of the
+ * transform there (ping-pong between two buffers, one __syncthreads per pass) and touches global
+ * memory exactly once on the way in and once on the way out.  It is the GPU counterpart of the
+ * reference's pass drivers c1fm1f_/cmfm1f_ (cfftpack/fftpack.c:2041, :5262), rfftf1_/mrftf1_
+ * (:13695, :10149) and of the pre/post loops of costf1_ (:6294), sintf1_ (:14828), cosqf1_ (:5665)
+ * and their *b1_ / m* twins -- but not a translation of them:
+ *
+ *  - passes are decimation-in-frequency Stockham autosort passes: every pass reads
+ *    x[b + (M/r) j] (unit stride across threads) and the last one leaves natural order;
+ *  - real transforms are done two sequences at a time as ONE complex transform
+ *    (z = x_a + i x_b), then separated through the Hermitian symmetry; this replaces the
+ *    r1f*kf_/mradf* half-complex passes and works for odd lengths too;
+ *  - cost/sint/cosq/sinq fold their pre/post-processing around that core inside the same CTA;
+ *    the serial dsum recurrences of the reference (:6393-6400, :14909-14915) become warp scans;
+ *  - lot/jump/inc (and a second batch level used by the four-step decomposition of long
+ *    transforms) are resolved in the loader/storer, which walk whichever of the element axis or
+ *    the batch axis is contiguous in memory so that global accesses stay coalesced.
+ */
+#ifndef CFB_ENGINE_CUH
+#define CFB_ENGINE_CUH
+#include "butterfly.cuh"
+#include "engine_types.h"
+
+namespace cfb {
+
+/* ------------------------------------------------------------------------------------------ */
+/* one radix-R pass over T sequences: src, dst are [T][ldz] complex arrays in shared memory       */
+template <int R, int DIR>
+__device__ __forceinline__ void pass_fixed(const cpx *__restrict__ src, cpx *__restrict__ dst, int T, int ldz, int M,
+                                           const PassDesc &pd, const cpx *__restrict__ tw, int tid, int nthr) {
+  const int nb = M / R;  // butterflies per sequence
+  const int total = nb * T;
+  const int s = pd.s, m = pd.m;
+  const cpx *twp = tw + pd.twoff;
+  for (int idx = tid; idx < total; idx += nthr) {
+    int t = idx / nb, b = idx - t * nb;
+    int p = b / s, q = b - p * s;
+    cpx a[R];
+    const cpx *sp = src + (size_t)t * ldz + b;
+#pragma unroll
+    for (int j = 0; j < R; ++j) a[j] = sp[j * nb];
+    Dft<R, DIR>::run(a);
+    cpx *dp = dst + (size_t)t * ldz + q + (size_t)s * R * p;
+    dp[0] = a[0];
+    if (m > 1) {
+#pragma unroll
+      for (int k = 1; k < R; ++k) dp[k * s] = ctw<DIR>(a[k], __ldg(twp + (k - 1) * m + p));
+    } else {
+#pragma unroll
+      for (int k = 1; k < R; ++k) dp[k * s] = a[k];
+    }
+  }
+}
+
+/* generic odd radix r (the reference's c1fgkf_/c1fgkb_, fftpack.c:1650/:1410): each thread produces the
+ * output pair (k, r-k) of one butterfly from the symmetric sums, O(r) work per output */
+template <int DIR>
+__device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *__restrict__ dst, int T, int ldz, int M,
+                                             const PassDesc &pd, const cpx *__restrict__ tw, int tid, int nthr) {
+  const int r = pd.radix, nb = M / r, s = pd.s, m = pd.m, half = (r + 1) / 2;
+  const int per = nb * half;  // work items per sequence: (k in [0, half)) x butterflies, butterflies fastest
+  const int total = per * T;
+  const cpx *twp = tw + pd.twoff;
+  const cpx *rt = tw + pd.rtoff;
+  for (int idx = tid; idx < total; idx += nthr) {
+    int t = idx / per, rem = idx - t * per;
+    int k = rem / nb, b = rem - k * nb;
+    int p = b / s, q = b - p * s;
+    const cpx *sp = src + (size_t)t * ldz + b;
+    cpx *dp = dst + (size_t)t * ldz + q + (size_t)s * r * p;
+    cpx a0 = sp[0];
+    if (k == 0) {
+      cpx acc = a0;
+      for (int j = 1; j < r; ++j) acc = cadd(acc, sp[j * nb]);
+      dp[0] = acc;
+    } else {
+      // X_k = a0 + sum_{j=1}^{half-1} [ c_jk (a_j + a_{r-j}) + DIR*i * s_jk (a_j - a_{r-j}) ],  X_{r-k}: minus sign
+      double ar = a0.x, ai = a0.y, br = 0.0, bi = 0.0;
+      int jk = 0;
+      for (int j = 1; j < half; ++j) {
+        jk += k;
+        if (jk >= r) jk -= r;
+        cpx w = __ldg(rt + jk);  // (cos, -sin)(2 pi jk / r)
+        cpx u = sp[j * nb], v = sp[(r - j) * nb];
+        double pr = u.x + v.x, pi = u.y + v.y, mr = u.x - v.x, mi = u.y - v.y;
+        ar = fma(w.x, pr, ar);
+        ai = fma(w.x, pi, ai);
+        br = fma(-w.y, mr, br);  // sin * (a_j - a_{r-j})
+        bi = fma(-w.y, mi, bi);
+      }
+      // DIR*i*(br + i bi) = DIR*(-bi + i br)
+      cpx xk, xc;
+      if (DIR < 0) {
+        xk = make_double2(ar + bi, ai - br);
+        xc = make_double2(ar - bi, ai + br);
+      } else {
+        xk = make_double2(ar - bi, ai + br);
+        xc = make_double2(ar + bi, ai - br);
+      }
+      if (m > 1) {
+        xk = ctw<DIR>(xk, __ldg(twp + (k - 1) * m + p));
+        xc = ctw<DIR>(xc, __ldg(twp + (r - k - 1) * m + p));
+      }
+      dp[(size_t)k * s] = xk;
+      dp[(size_t)(r - k) * s] = xc;
+    }
+  }
+}
+
+template <int DIR>
+__device__ __forceinline__ void run_passes(cpx *&cur, cpx *&oth, const EngineParams &P, int tid, int nthr) {
+  for (int ip = 0; ip < P.nf; ++ip) {
+    const PassDesc &pd = P.pass[ip];
+    switch (pd.radix) {
+      case 2: pass_fixed<2, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
+      case 3: pass_fixed<3, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
+      case 4: pass_fixed<4, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
+      case 5: pass_fixed<5, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
+      case 8: pass_fixed<8, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
+      case 16: pass_fixed<16, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
+      default: pass_generic<DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
+    }
+    __syncthreads();
+    cpx *t = cur;
+    cur = oth;
+    oth = t;
+  }
+}
+
+__device__ __forceinline__ long long batch_off(const Addr &a, long long g) {
+  long long hi = g / a.nlo, lo = g - hi * a.nlo;
+  return hi * a.jump_hi + lo * a.jump_lo;
+}
+
+/* split a linear work index over a [rows][len] tile so that consecutive threads follow the axis that is
+ * contiguous in global memory */
+__device__ __forceinline__ void tile_index(int idx, int rows, int len, int lanes_t, int &row, int &e) {
+  if (lanes_t) {
+    e = idx / rows;
+    row = idx - e * rows;
+  } else {
+    row = idx / len;
+    e = idx - row * len;
+  }
+}
+
+/* ---- warp helpers (one warp works on one real sequence in the pre/post phases) ---- */
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+/* exclusive prefix over the lanes of a warp */
+__device__ __forceinline__ double warp_excl_scan(double v, int lane) {
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  return inc - v;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* forward real core, output side: Z = FFT(x_a + i x_b) (unscaled) -> FFTPACK half-complex rows ha, hb
+ * scaled like rfftf1_ (fftpack.c:13818-13853): h[0]=X0/M, h[2f-1]=2Re X_f/M, h[2f]=-2Im X_f/M, h[M-1]=X_{M/2}/M */
+__device__ __forceinline__ void split_pair(const cpx *__restrict__ z, double *__restrict__ ha, double *__restrict__ hb,
+                                           int M, int f) {
+  const double sc = 1.0 / (double)M;
+  if (f == 0) {
+    cpx z0 = z[0];
+    ha[0] = z0.x * sc;
+    hb[0] = z0.y * sc;
+  } else if (2 * f < M) {
+    cpx u = z[f], v = z[M - f];
+    ha[2 * f - 1] = (u.x + v.x) * sc;
+    ha[2 * f] = -(u.y - v.y) * sc;
+    hb[2 * f - 1] = (u.y + v.y) * sc;
+    hb[2 * f] = (u.x - v.x) * sc;
+  } else if (2 * f == M) {
+    cpx u = z[f];
+    ha[M - 1] = u.x * sc;
+    hb[M - 1] = u.y * sc;
+  }
+}
+
+/* backward real core, input side: half-complex rows ha, hb -> Z with z = x_a + i x_b after the backward FFT
+ * (rfftb1_, fftpack.c:13517: x_t = h0 + sum h[2f-1] cos + h[2f] sin (+ (-1)^t h[M-1])) */
+__device__ __forceinline__ void build_pair(cpx *__restrict__ z, const double *__restrict__ ha,
+                                           const double *__restrict__ hb, int M, int f) {
+  if (f == 0) {
+    z[0] = make_double2(ha[0], hb[0]);
+  } else if (2 * f < M) {
+    double a1 = 0.5 * ha[2 * f - 1], a2 = 0.5 * ha[2 * f], b1 = 0.5 * hb[2 * f - 1], b2 = 0.5 * hb[2 * f];
+    z[f] = make_double2(a1 + b2, b1 - a2);
+    z[M - f] = make_double2(a1 - b2, b1 + a2);
+  } else if (2 * f == M) {
+    z[f] = make_double2(ha[M - 1], hb[M - 1]);
+  }
+}
+
+/* ---- kind-specific pre-processing of ONE real sequence, done by one warp.
+ * x: the loaded sequence (length n, unit stride).  Forward-core kinds write u (length M) into the re or im
+ * lane of the complex row (zc, stride 2).  Backward-core kinds write the half-complex row h (unit stride). */
+__device__ __forceinline__ void pre_forward_core(int kind, int dir, int n, int M, const double *__restrict__ x,
+                                                 double *__restrict__ zc, const double *__restrict__ trig, double *dsum,
+                                                 int lane) {
+  if (kind == K_RFFT) {
+    for (int j = lane; j < n; j += 32) zc[2 * j] = x[j];
+  } else if (kind == K_COST) {
+    // costf1_/costb1_ pre-fold (fftpack.c:6355-6377, :6222-6244); trig[j] = 2 sin(j pi/M), trig[M + j] = 2 cos(j pi/M)
+    const int ns2 = n / 2;
+    const double e = (dir > 0) ? 2.0 : 1.0;  // backward doubles the end points first
+    double part = 0.0;
+    for (int j = 1 + lane; j < ns2; j += 32) {
+      int jc = n - 1 - j;
+      double t1 = x[j] + x[jc], t2 = x[j] - x[jc];
+      part = fma(trig[M + j], t2, part);
+      t2 = trig[j] * t2;
+      zc[2 * j] = t1 - t2;
+      if (jc < M) zc[2 * jc] = t1 + t2;
+    }
+    part = warp_sum(part);
+    if (lane == 0) {
+      double x0 = e * x[0], xn = e * x[n - 1];
+      *dsum = (x0 - xn) + part;
+      zc[0] = x0 + xn;
+      if (n & 1) zc[2 * ns2] = x[ns2] + x[ns2];
+    }
+  } else if (kind == K_SINT) {
+    // sintf1_ pre (fftpack.c:14873-14888); trig[k-1] = 2 sin(k pi/(n+1))
+    const int ns2 = n / 2;
+    for (int k = 1 + lane; k <= ns2; k += 32) {
+      int kc = n + 1 - k;
+      double t1 = x[k - 1] - x[kc - 1], t2 = trig[k - 1] * (x[k - 1] + x[kc - 1]);
+      zc[2 * k] = t1 + t2;
+      zc[2 * kc] = t2 - t1;
+    }
+    if (lane == 0) {
+      zc[0] = 0.0;
+      if (n & 1) zc[2 * (ns2 + 1)] = 4.0 * x[ns2];
+    }
+  } else {  // K_COSQ / K_SINQ forward: cosqf1_ pre (fftpack.c:5693-5717); trig[i] = cos((i+1) pi/(2n))
+    const int ns2 = (n + 1) / 2;
+    for (int j = 1 + lane; j < ns2; j += 32) {
+      int jc = n - j;
+      double a = x[j] + x[jc], b = x[j] - x[jc];
+      zc[2 * j] = fma(trig[j - 1], b, trig[jc - 1] * a);
+      zc[2 * jc] = fma(trig[j - 1], a, -(trig[jc - 1] * b));
+    }
+    if (lane == 0) {
+      zc[0] = x[0];
+      if (!(n & 1)) zc[2 * ns2] = trig[ns2 - 1] * (x[ns2] + x[ns2]);
+    }
+  }
+}
+
+__device__ __forceinline__ void pre_backward_core(int kind, int n, const double *__restrict__ x, double *__restrict__ h,
+                                                  int lane) {
+  if (kind == K_RFFT) {
+    for (int j = lane; j < n; j += 32) h[j] = x[j];
+  } else {  // cosqb1_ pre (fftpack.c:5604-5616)
+    for (int i0 = 2 + 2 * lane; i0 < n; i0 += 64) {
+      double a = x[i0 - 1], b = x[i0];
+      h[i0 - 1] = 0.5 * (a + b);
+      h[i0] = 0.5 * (a - b);
+    }
+    if (lane == 0) {
+      h[0] = 0.5 * x[0];
+      if (!(n & 1)) h[n - 1] = 0.5 * x[n - 1];
+    }
+  }
+}
+
+/* ---- kind-specific post-processing of ONE real sequence by one warp: s -> y (both unit stride).
+ * s is the half-complex row h (forward core, length M) or the real sequence u (backward core). */
+__device__ __forceinline__ void post_sequence(int kind, int dir, int n, int M, const double *__restrict__ s,
+                                              double *__restrict__ y, const double *__restrict__ trig, double dsum,
+                                              int lane) {
+  if (kind == K_RFFT) {
+    for (int j = lane; j < n; j += 32) y[j] = s[j];
+  } else if (kind == K_COST) {
+    // costf1_ post (fftpack.c:6386-6407) / costb1_ post (:6253-6283):
+    //   y[0] = c0 h[0]; y[2m] = c1 h'[2m-1]; y[2m-1] = D + sum_{m'<m} c1 h'[2m'];  h' = h with h[M-1] doubled if M even
+    const double c0 = dir < 0 ? 0.5 : 0.5 * (double)M, c1 = dir < 0 ? 0.5 : 0.25 * (double)M;
+    const double D = dir < 0 ? dsum / (double)M : 0.5 * dsum;
+    const int last = (M % 2 == 0) ? M - 1 : -1;
+    const int cnt = n / 2;  // odd output indices 2m-1, m = 1..cnt
+    const int chunk = (cnt + 31) / 32;
+    const int m_lo = 1 + lane * chunk, m_hi = min(m_lo + chunk, cnt + 1);
+    double loc = 0.0;  // sum over my m of c1*h'[2m]
+    for (int mm = m_lo; mm < m_hi; ++mm) {
+      int i = 2 * mm;
+      if (i < M) loc += c1 * (i == last ? 2.0 * s[i] : s[i]);
+    }
+    double run = D + warp_excl_scan(loc, lane);
+    for (int mm = m_lo; mm < m_hi; ++mm) {
+      int i = 2 * mm;
+      y[i - 1] = run;
+      if (i < M) run += c1 * (i == last ? 2.0 * s[i] : s[i]);
+      if (i < n) y[i] = c1 * ((i - 1) == last ? 2.0 * s[i - 1] : s[i - 1]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      y[0] = c0 * s[0];
+      if (dir < 0) y[n - 1] *= 0.5;
+    }
+  } else if (kind == K_SINT) {
+    // sintf1_ post (fftpack.c:14898-14919): y[2m] = sc h[0] + sum_{m'<=m} sc h[2m'-1]; y[2m-1] = sc h[2m]
+    const double sc = dir < 0 ? 0.5 : 0.25 * (double)M;
+    const int cnt = (n - 1) / 2;  // even output indices 2m, m = 1..cnt
+    const int chunk = (cnt + 31) / 32;
+    const int m_lo = 1 + lane * chunk, m_hi = min(m_lo + chunk, cnt + 1);
+    double loc = 0.0;
+    for (int mm = m_lo; mm < m_hi; ++mm) loc += sc * s[2 * mm - 1];
+    double run = sc * s[0] + warp_excl_scan(loc, lane);
+    for (int mm = m_lo; mm < m_hi; ++mm) {
+      run += sc * s[2 * mm - 1];
+      y[2 * mm] = run;
+      y[2 * mm - 1] = sc * s[2 * mm];
+    }
+    if (lane == 0) {
+      y[0] = sc * s[0];
+      if (!(n & 1)) y[n - 1] = sc * s[n];
+    }
+  } else if (dir < 0) {  // cosqf1_ post (fftpack.c:5731-5738)
+    for (int i0 = 2 + 2 * lane; i0 < n; i0 += 64) {
+      double a = s[i0 - 1], b = s[i0];
+      y[i0 - 1] = 0.5 * (a + b);
+      y[i0] = 0.5 * (a - b);
+    }
+    if (lane == 0) {
+      y[0] = s[0];
+      if (!(n & 1)) y[n - 1] = s[n - 1];
+    }
+  } else {  // cosqb1_ post (fftpack.c:5625-5652)
+    const int ns2 = (n + 1) / 2;
+    for (int j = 1 + lane; j < ns2; j += 32) {
+      int jc = n - j;
+      double p = fma(trig[j - 1], s[jc], trig[jc - 1] * s[j]);
+      double q = fma(trig[j - 1], s[j], -(trig[jc - 1] * s[jc]));
+      y[j] = p + q;
+      y[jc] = p - q;
+    }
+    if (lane == 0) {
+      y[0] = s[0] + s[0];
+      if (!(n & 1)) y[ns2] = trig[ns2 - 1] * (s[ns2] + s[ns2]);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(CFB_ENGINE_THREADS) engine_kernel(const EngineParams P) {
+  CFB_DYN_SMEM(smem_raw);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int T = P.T, ldz = P.ldz, M = P.M, n = P.n;
+  cpx *zA = (cpx *)smem_raw;
+  cpx *zB = zA + (size_t)T * ldz;
+  const long long g0 = (long long)blockIdx.x * T;
+
+  if (P.kind == K_C2C) {
+    /* ---- load: global -> zA ---- */
+    const cpx *in = (const cpx *)P.in;
+    const int total = T * M;
+    for (int idx = tid; idx < total; idx += nthr) {
+      int t, e;
+      tile_index(idx, T, M, P.ain.lanes_t, t, e);
+      long long g = g0 + t;
+      cpx v = make_double2(0.0, 0.0);
+      if (g < P.lot) {
+        const cpx *p = in + batch_off(P.ain, g) + (long long)e * P.ain.inc;
+        if (P.aligned16) v = *p;
+        else {
+          v.x = ((const double *)p)[0];
+          v.y = ((const double *)p)[1];
+        }
+      }
+      zA[(size_t)t * ldz + e] = v;
+    }
+    __syncthreads();
+    cpx *cur = zA, *oth = zB;
+    if (P.dir < 0) run_passes<-1>(cur, oth, P, tid, nthr);
+    else run_passes<1>(cur, oth, P, tid, nthr);
+    /* ---- store: cur -> global ---- */
+    cpx *out = (cpx *)P.out;
+    for (int idx = tid; idx < total; idx += nthr) {
+      int t, e;
+      tile_index(idx, T, M, P.aout.lanes_t, t, e);
+      long long g = g0 + t;
+      if (g >= P.lot) continue;
+      cpx v = cur[(size_t)t * ldz + e];
+      v.x *= P.scale;
+      v.y *= P.scale;
+      if (P.fs_tw) {
+        long long lo = g % P.aout.nlo;
+        cpx w = __ldg(P.fs_tw + (int)((lo * e) % P.fs_n));
+        v = (P.dir < 0) ? cmul(v, w) : cmulc(v, w);
+      }
+      cpx *p = out + batch_off(P.aout, g) + (long long)e * P.aout.inc;
+      if (P.aligned16) *p = v;
+      else {
+        ((double *)p)[0] = v.x;
+        ((double *)p)[1] = v.y;
+      }
+    }
+    return;
+  }
+
+  /* ---- real kinds: T pairs of sequences ---- */
+  const int ldx = P.ldx, rows = 2 * T;
+  double *xs = (double *)(zB + (size_t)T * ldz);  // [2T][ldx]
+  double *dsum = xs + (size_t)rows * ldx;          // [2T]
+  const int kind = P.kind, dir = P.dir;
+  const bool fwd_core = !((kind == K_RFFT || kind == K_COSQ || kind == K_SINQ) && dir > 0);
+  const long long s0 = 2 * g0;  // first sequence of this CTA
+  const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+  {
+    /* load: global -> xs.  sinq reverses the sequence (forward) or flips odd entries (backward),
+     * sinqf1_/sinqb1_ fftpack.c:14247-14266 */
+    const double *in = (const double *)P.in;
+    const int total = rows * n;
+    for (int idx = tid; idx < total; idx += nthr) {
+      int r, e;
+      tile_index(idx, rows, n, P.ain.lanes_t, r, e);
+      long long g = s0 + r;
+      double v = 0.0;
+      if (g < P.lot) v = in[batch_off(P.ain, g) + (long long)e * P.ain.inc];
+      int ed = e;
+      if (kind == K_SINQ) {
+        if (dir < 0) ed = n - 1 - e;
+        else if (e & 1) v = -v;
+      }
+      xs[(size_t)r * ldx + ed] = v;
+    }
+  }
+  __syncthreads();
+  cpx *cur = zA, *oth = zB;
+  if (fwd_core) {
+    for (int r = warp; r < rows; r += nwarp)
+      pre_forward_core(kind, dir, n, M, xs + (size_t)r * ldx, (double *)(zA + (size_t)(r >> 1) * ldz) + (r & 1), P.trig,
+                       dsum + r, lane);
+    __syncthreads();
+    run_passes<-1>(cur, oth, P, tid, nthr);
+    /* split: cur -> half-complex rows in oth (row pitch ldz doubles) */
+    double *hs = (double *)oth;
+    const int nfq = M / 2 + 1;
+    for (int idx = tid; idx < T * nfq; idx += nthr) {
+      int t = idx / nfq, f = idx - t * nfq;
+      split_pair(cur + (size_t)t * ldz, hs + (size_t)(2 * t) * ldz, hs + (size_t)(2 * t + 1) * ldz, M, f);
+    }
+    __syncthreads();
+    for (int r = warp; r < rows; r += nwarp)
+      post_sequence(kind, dir, n, M, hs + (size_t)r * ldz, xs + (size_t)r * ldx, P.trig, dsum[r], lane);
+  } else {
+    double *hs = (double *)zB;
+    for (int r = warp; r < rows; r += nwarp) pre_backward_core(kind, n, xs + (size_t)r * ldx, hs + (size_t)r * ldz, lane);
+    __syncthreads();
+    const int nfq = M / 2 + 1;
+    for (int idx = tid; idx < T * nfq; idx += nthr) {
+      int t = idx / nfq, f = idx - t * nfq;
+      build_pair(zA + (size_t)t * ldz, hs + (size_t)(2 * t) * ldz, hs + (size_t)(2 * t + 1) * ldz, M, f);
+    }
+    __syncthreads();
+    run_passes<1>(cur, oth, P, tid, nthr);
+    /* extract: re/im of cur -> real rows in oth */
+    double *us = (double *)oth;
+    for (int idx = tid; idx < T * M; idx += nthr) {
+      int t = idx / M, e = idx - t * M;
+      cpx v = cur[(size_t)t * ldz + e];
+      us[(size_t)(2 * t) * ldz + e] = v.x;
+      us[(size_t)(2 * t + 1) * ldz + e] = v.y;
+    }
+    __syncthreads();
+    for (int r = warp; r < rows; r += nwarp)
+      post_sequence(kind, dir, n, M, us + (size_t)r * ldz, xs + (size_t)r * ldx, P.trig, 0.0, lane);
+  }
+  __syncthreads();
+  {
+    double *out = (double *)P.out;
+    const int total = rows * n;
+    for (int idx = tid; idx < total; idx += nthr) {
+      int r, e;
+      tile_index(idx, rows, n, P.aout.lanes_t, r, e);
+      long long g = s0 + r;
+      if (g >= P.lot) continue;
+      int es = e;
+      double sg = 1.0;
+      if (kind == K_SINQ) {
+        if (dir < 0) sg = (e & 1) ? -1.0 : 1.0;
+        else es = n - 1 - e;
+      }
+      out[batch_off(P.aout, g) + (long long)e * P.aout.inc] = sg * xs[(size_t)r * ldx + es];
+    }
+  }
+}
+
+/* closed forms for the lengths the reference special-cases (costf1_ n=2,3 fftpack.c:6339-6353; sintf1_ n=2
+ * :14858-14866; cosqf1_ n=2 :5498-5502; the backward twins) -- one thread per sequence */
+struct TinyParams {
+  int kind, dir, n;
+  long long lot;
+  Addr a;
+  double *x;
+};
+__global__ void __launch_bounds__(128) tiny_kernel(const TinyParams P) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.lot) return;
+  double *x = P.x + batch_off(P.a, g);
+  const long long inc = P.a.inc;
+  const bool fwd = P.dir < 0;
+  if (P.kind == K_COST && P.n == 2) {
+    double a = x[0], b = x[inc];
+    if (fwd) {
+      x[0] = (a + b) * 0.5;
+      x[inc] = (a - b) * 0.5;
+    } else {
+      x[0] = a + b;
+      x[inc] = a - b;
+    }
+  } else if (P.kind == K_COST && P.n == 3) {
+    double a = x[0], b = x[inc], c = x[2 * inc], s = a + c;
+    if (fwd) {
+      double tb = b + b;
+      x[inc] = (a - c) * 0.5;
+      x[0] = (s + tb) * 0.25;
+      x[2 * inc] = (s - tb) * 0.25;
+    } else {
+      x[inc] = a - c;
+      x[0] = s + b;
+      x[2 * inc] = s - b;
+    }
+  } else if (P.kind == K_SINT && P.n == 2) {
+    const double c = fwd ? 0.57735026918962576450914878050196 : 0.86602540378443864676372317075294;
+    double a = x[0], b = x[inc];
+    x[0] = c * (a + b);
+    x[inc] = c * (a - b);
+  } else if ((P.kind == K_COSQ || P.kind == K_SINQ) && P.n == 2) {
+    const double h = 0.70710678118654752440084436210485;
+    double a = x[0], b = x[inc];
+    if (P.kind == K_SINQ) {
+      if (fwd) {  // reverse, cosq, negate odd entry
+        double t = a;
+        a = b;
+        b = t;
+      } else {
+        b = -b;
+      }
+    }
+    double y0, y1;
+    if (fwd) {
+      y0 = a * 0.5 + h * b;
+      y1 = a * 0.5 - h * b;
+    } else {
+      y0 = a + b;
+      y1 = h * (a - b);
+    }
+    if (P.kind == K_SINQ) {
+      if (fwd) y1 = -y1;
+      else {
+        double t = y0;
+        y0 = y1;
+        y1 = t;
+      }
+    }
+    x[0] = y0;
+    x[inc] = y1;
+  }
+}
+
+}  // namespace cfb
+#endif

@@ -1,0 +1,52 @@
+/* engine_types.h -- plain-data descriptions shared by the plans (host) and the engine kernel (device). */
+#ifndef CFB_ENGINE_TYPES_H
+#define CFB_ENGINE_TYPES_H
+#include "cfb_rt.h"
+
+namespace cfb {
+
+typedef double2 cpx;
+
+enum Kind { K_C2C = 0, K_RFFT = 1, K_COST = 2, K_SINT = 3, K_COSQ = 4, K_SINQ = 5 };
+
+#define CFB_MAXPASS 24
+#define CFB_ENGINE_THREADS 256
+
+struct PassDesc {
+  int radix;  // 2,3,4,5 or a generic odd prime
+  int s;      // product of the radices of earlier passes
+  int m;      // remaining length / radix
+  int twoff;  // offset of this pass's twiddles in the plan table, laid out [k-1][p], p < m
+  int rtoff;  // generic radix only: offset of the table exp(-2 pi i j / radix), j < radix
+};
+
+/* element (g, e) of a batch lives at  (g / nlo) * jump_hi + (g % nlo) * jump_lo + e * inc  (units: elements) */
+struct Addr {
+  long long inc, jump_lo, jump_hi;
+  int nlo;
+  int lanes_t;  // 1: consecutive threads walk the batch axis (jump_lo is the small stride)
+};
+
+struct EngineParams {
+  int kind, dir;  // dir: -1 forward, +1 backward (user-level direction)
+  int n;          // user sequence length
+  int M;          // length of the complex core transform (n, n-1 for cost, n+1 for sint)
+  int nf;
+  int T;    // complex sequences (c2c) or PAIRS of real sequences (other kinds) per CTA
+  int ldz;  // row pitch of the complex buffers (odd, >= M)
+  int ldx;  // row pitch of the real staging rows (odd, >= n + 1)
+  int aligned16;  // c2c: in and out are 16-byte aligned
+  long long lot;  // sequences in the batch
+  Addr ain, aout;
+  const void *in;
+  void *out;
+  const cpx *tw;       // twiddles of all passes, forward convention
+  const double *trig;  // kind tables (see plan.cpp)
+  double scale;        // c2c: factor applied on store
+  const cpx *fs_tw;    // four-step: multiply element e of sequence g by fs_tw[((g % nlo) * e) % fs_n] on store
+  int fs_n;
+  PassDesc pass[CFB_MAXPASS];
+};
+
+}  // namespace cfb
+#endif

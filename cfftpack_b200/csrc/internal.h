@@ -1,0 +1,48 @@
+/* internal.h -- host-side plumbing shared by the translation units of libcfftpack_b200. */
+#ifndef CFB_INTERNAL_H
+#define CFB_INTERNAL_H
+#include "cfb_rt.h"
+
+namespace cfb {
+
+void set_error(const char *fmt, ...);
+const char *last_error();
+bool cuda_ok(cudaError_t e, const char *what);
+#define CFB_CUDA(call)                     \
+  do {                                     \
+    if (!cfb::cuda_ok((call), #call)) return false; \
+  } while (0)
+
+cudaStream_t current_stream();
+void set_current_stream(cudaStream_t s);
+void count_launch(unsigned long long k = 1);
+unsigned long long launch_count();
+
+/* true once a CUDA device is usable; otherwise prints one loud line to stderr (there is no CPU path) */
+bool device_ready();
+int sm_count();
+
+/* grow-only per-thread device scratch (four-step intermediates, staging of host arrays) */
+void *scratch_get(int slot, size_t bytes);
+void scratch_release_all();
+
+/* ---- transform drivers (dispatch.cu).  Pointers are DEVICE pointers; strides in elements. ---- */
+bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void *c);
+bool run_real(int kind, int n, long long lot, long long inc, long long jump, int dir, double *x);
+bool run_c2c_2d(int ldim, int l, int m, int dir, void *c);
+
+/* largest core length the single-kernel paths take (for tests and docs) */
+int engine_max_c2c();
+int engine_max_real();
+
+/* ---- host wsave initialisers (wsave_init.cpp), bit-compatible with the reference ---- */
+int log2_floor_ref(int n);  // the literal (int)(log((double)n)/log(2.0)) of fftpack.c:2221
+void wsave_init_complex(int n, double *wsave);
+void wsave_init_real(int n, double *wsave);
+void wsave_init_cost(int n, double *wsave);
+void wsave_init_sint(int n, double *wsave);
+void wsave_init_cosq(int n, double *wsave);
+bool strides_consistent(int inc, int jump, int n, int lot);  // xercon_, fftpack.c:15210
+
+}  // namespace cfb
+#endif

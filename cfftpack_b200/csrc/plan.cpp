@@ -1,0 +1,261 @@
+/* plan.cpp -- builds and caches the device-resident plans declared in plan.h. */
+#include "plan.h"
+
+#include <math.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "internal.h"
+
+namespace cfb {
+
+void unit_root(long long num, long long den, double *re, double *im) {
+  // reduce to the first octant so that cosl/sinl see a small argument; exact symmetries elsewhere
+  num %= den;
+  if (num < 0) num += den;
+  // angle = 2 pi num/den; work with eighths of a turn: t = 8 num / den
+  long long n8 = 8 * num;
+  int oct = (int)(n8 / den);       // 0..7
+  long long rem = n8 - oct * den;  // angle within the octant = (pi/4) rem/den
+  const long double PI4 = 0.78539816339744830961566084581987572L;
+  long double c, s;
+  if (oct & 1) {  // measure back from the next octant boundary to stay in [0, pi/4]
+    long double a = PI4 * (long double)(den - rem) / (long double)den;
+    c = cosl(a);
+    s = sinl(a);
+  } else {
+    long double a = PI4 * (long double)rem / (long double)den;
+    c = cosl(a);
+    s = sinl(a);
+  }
+  long double cr, sr;  // cos, sin of the full angle
+  switch (oct) {
+    case 0: cr = c; sr = s; break;
+    case 1: cr = s; sr = c; break;
+    case 2: cr = -s; sr = c; break;
+    case 3: cr = -c; sr = s; break;
+    case 4: cr = -c; sr = -s; break;
+    case 5: cr = -s; sr = -c; break;
+    case 6: cr = s; sr = -c; break;
+    default: cr = c; sr = -s; break;
+  }
+  *re = (double)cr;
+  *im = (double)(-sr);
+}
+
+int engine_factor(int M, int *radix) {
+  int nf = 0, a = 0;
+  while (M % 2 == 0) {
+    M /= 2;
+    ++a;
+  }
+  // power of two: as many 16s as possible, the remainder as 8/4/2 (no pass smaller than needed)
+  switch (a % 4) {
+    case 1:
+      if (a >= 5) {
+        radix[nf++] = 8;
+        radix[nf++] = 4;
+        a -= 5;
+      } else {
+        radix[nf++] = 2;
+        a -= 1;
+      }
+      break;
+    case 2: radix[nf++] = 4; a -= 2; break;
+    case 3: radix[nf++] = 8; a -= 3; break;
+    default: break;
+  }
+  while (a >= 4) {
+    radix[nf++] = 16;
+    a -= 4;
+  }
+  while (M % 5 == 0) {
+    radix[nf++] = 5;
+    M /= 5;
+  }
+  while (M % 3 == 0) {
+    radix[nf++] = 3;
+    M /= 3;
+  }
+  for (int p = 7; (long long)p * p <= M; p += 2)
+    while (M % p == 0) {
+      radix[nf++] = p;
+      M /= p;
+    }
+  if (M > 1) radix[nf++] = M;
+  return nf;
+}
+
+namespace {
+std::mutex g_mu;
+struct Key {
+  int dev, a, b;
+  bool operator<(const Key &o) const { return dev != o.dev ? dev < o.dev : a != o.a ? a < o.a : b < o.b; }
+};
+std::map<Key, CorePlan *> g_core;
+std::map<Key, TrigPlan *> g_trig;
+std::map<Key, RootPlan *> g_root;
+
+int cur_dev() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+
+template <class T>
+T *upload(const std::vector<T> &h) {
+  T *d = nullptr;
+  size_t bytes = (h.size() ? h.size() : 1) * sizeof(T);
+  if (!cuda_ok(cudaMalloc((void **)&d, bytes), "cudaMalloc(plan)")) return nullptr;
+  if (h.size() && !cuda_ok(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy(plan)")) {
+    cudaFree(d);
+    return nullptr;
+  }
+  return d;
+}
+}  // namespace
+
+const CorePlan *get_core_plan(int M) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Key k{cur_dev(), M, 0};
+  auto it = g_core.find(k);
+  if (it != g_core.end()) return it->second;
+  CorePlan *pl = new CorePlan();
+  pl->M = M;
+  int radix[64];
+  pl->nf = engine_factor(M, radix);
+  if (pl->nf > CFB_MAXPASS) {
+    set_error("length %d needs %d passes (max %d)", M, pl->nf, CFB_MAXPASS);
+    delete pl;
+    return nullptr;
+  }
+  std::vector<cpx> tw;
+  int s = 1, cur = M;
+  for (int i = 0; i < pl->nf; ++i) {
+    int r = radix[i], m = cur / r;
+    PassDesc &pd = pl->pass[i];
+    pd.radix = r;
+    pd.s = s;
+    pd.m = m;
+    pd.twoff = (int)tw.size();
+    pd.rtoff = 0;
+    if (m > 1)
+      for (int kk = 1; kk < r; ++kk)
+        for (int p = 0; p < m; ++p) {
+          cpx w;
+          unit_root((long long)p * kk, cur, &w.x, &w.y);
+          tw.push_back(w);
+        }
+    if (r > 5 && r != 8 && r != 16) {
+      pd.rtoff = (int)tw.size();
+      for (int j = 0; j < r; ++j) {
+        cpx w;
+        unit_root(j, r, &w.x, &w.y);
+        tw.push_back(w);
+      }
+    }
+    if (r > pl->max_radix) pl->max_radix = r;
+    s *= r;
+    cur = m;
+  }
+  pl->tw_count = tw.size();
+  pl->d_tw = upload(tw);
+  if (!pl->d_tw) {
+    delete pl;
+    return nullptr;
+  }
+  g_core[k] = pl;
+  return pl;
+}
+
+const TrigPlan *get_trig_plan(int kind, int n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Key k{cur_dev(), kind, n};
+  auto it = g_trig.find(k);
+  if (it != g_trig.end()) return it->second;
+  TrigPlan *pl = new TrigPlan();
+  pl->kind = kind;
+  pl->n = n;
+  std::vector<double> t;
+  const long double PI = 3.14159265358979323846264338327950288L;
+  if (kind == K_COST) {
+    // t[j] = 2 sin(j pi/M), t[M + j] = 2 cos(j pi/M), j < M   (cost1i_, fftpack.c:6145-6150)
+    int M = n - 1;
+    pl->M = M;
+    t.resize(2 * (size_t)M);
+    for (int j = 0; j < M; ++j) {
+      double c, s;  // exp(-2 pi i j/(2M)) = (cos, -sin)(j pi/M)
+      unit_root(j, 2LL * M, &c, &s);
+      t[j] = -2.0 * s;
+      t[M + j] = 2.0 * c;
+    }
+  } else if (kind == K_SINT) {
+    // t[k-1] = 2 sin(k pi/(n+1))   (sint1i_, fftpack.c:14703-14705)
+    int M = n + 1;
+    pl->M = M;
+    t.resize(n / 2 + 1);
+    for (int kk = 1; kk <= n / 2; ++kk) {
+      double c, s;
+      unit_root(kk, 2LL * M, &c, &s);
+      t[kk - 1] = -2.0 * s;
+    }
+  } else {
+    // t[i] = cos((i+1) pi/(2n))   (cosq1i_, fftpack.c:5550-5557)
+    pl->M = n;
+    t.resize(n);
+    for (int i = 0; i < n; ++i) {
+      double c, s;
+      unit_root(i + 1, 4LL * n, &c, &s);
+      t[i] = c;
+    }
+  }
+  (void)PI;
+  pl->d_trig = upload(t);
+  if (!pl->d_trig) {
+    delete pl;
+    return nullptr;
+  }
+  g_trig[k] = pl;
+  return pl;
+}
+
+const RootPlan *get_root_plan(int n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Key k{cur_dev(), n, 0};
+  auto it = g_root.find(k);
+  if (it != g_root.end()) return it->second;
+  RootPlan *pl = new RootPlan();
+  pl->n = n;
+  std::vector<cpx> w(n);
+  for (int j = 0; j < n; ++j) unit_root(j, n, &w[j].x, &w[j].y);
+  pl->d_w = upload(w);
+  if (!pl->d_w) {
+    delete pl;
+    return nullptr;
+  }
+  g_root[k] = pl;
+  return pl;
+}
+
+void release_plans() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto &kv : g_core) {
+    cudaFree(kv.second->d_tw);
+    delete kv.second;
+  }
+  for (auto &kv : g_trig) {
+    cudaFree(kv.second->d_trig);
+    delete kv.second;
+  }
+  for (auto &kv : g_root) {
+    cudaFree(kv.second->d_w);
+    delete kv.second;
+  }
+  g_core.clear();
+  g_trig.clear();
+  g_root.clear();
+}
+
+}  // namespace cfb

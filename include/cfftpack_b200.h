@@ -1,0 +1,94 @@
+/*
+ * cfftpack_b200.h -- C ABI of libcfftpack_b200.so, the B200 (sm_100a) implementation of the FFTPACK 5.1
+ * transform path of zywina/cfftpack.
+ *
+ * The entry points below are the ones the reference exports from cfftpack/fftpack.c and declares in
+ * cfftpack/fftpack.h:80-169 (plus the batched *m* routines it exports without declaring).  Names, argument
+ * order, argument meaning and ier codes are the reference's: Fortran convention, every scalar by pointer,
+ * arrays by pointer, status through *ier, return value always 0.  A program written against fftpack.h
+ * relinks against this library unchanged.
+ *
+ * Data arrays (c / r / x) may be HOST pointers (the library stages them through HBM: copy in, transform,
+ * copy out, synchronous like the reference) or DEVICE pointers (transformed in place, asynchronously on the
+ * stream set with cfb200_set_stream, default stream otherwise).  wsave is always a host array; work is
+ * accepted for length checking and never touched.
+ *
+ * ier: 0 ok; 1 data array too short; 2 lensav too short; 3 lenwrk too short; 4 (inc,jump,n,lot)
+ * inconsistent; 5 l > ldim (2-D); 20 failure in an inner call; -1 CUDA failure (see cfb200_last_error()).
+ * Deliberate deviation: on ier != 0 no data is touched, for every routine.
+ */
+#ifndef CFFTPACK_B200_H
+#define CFFTPACK_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef double fft_real_t; /* cfftpack/fftpack.h:59-64 (FP64 build) */
+typedef struct {
+  fft_real_t r, i;
+} fft_complex_t; /* cfftpack/fftpack.h:72-75 */
+
+/* ---- complex 1-D: cfftpack/fftpack.h:83-94, fftpack.c:2151 (cfft1b_), :2199 (cfft1f_), :2247 (cfft1i_) ---- */
+int cfft1i_(int *n, fft_real_t *wsave, int *lensav, int *ier);
+int cfft1f_(int *n, int *inc, fft_complex_t *c, int *lenc, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+int cfft1b_(int *n, int *inc, fft_complex_t *c, int *lenc, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+
+/* ---- complex batched: fftpack.c:2609 (cfftmi_), :2554 (cfftmf_), :2499 (cfftmb_); exported, not in fftpack.h ---- */
+int cfftmi_(int *n, fft_real_t *wsave, int *lensav, int *ier);
+int cfftmf_(int *lot, int *jump, int *n, int *inc, fft_complex_t *c, int *lenc, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+int cfftmb_(int *lot, int *jump, int *n, int *inc, fft_complex_t *c, int *lenc, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+
+/* ---- complex 2-D: cfftpack/fftpack.h:97-109, fftpack.c:2443 (cfft2i_), :2363 (cfft2f_), :2285 (cfft2b_) ---- */
+int cfft2i_(int *l, int *m, fft_real_t *wsave, int *lensav, int *ier);
+int cfft2f_(int *ldim, int *l, int *m, fft_complex_t *c, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+int cfft2b_(int *ldim, int *l, int *m, fft_complex_t *c, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+
+/* ---- real 1-D: cfftpack/fftpack.h:150-157, fftpack.c:13076 (rfft1i_), :13030 (rfft1f_), :12984 (rfft1b_) ---- */
+int rfft1i_(int *n, fft_real_t *wsave, int *lensav, int *ier);
+int rfft1f_(int *n, int *inc, fft_real_t *r, int *lenr, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+int rfft1b_(int *n, int *inc, fft_real_t *r, int *lenr, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+
+/* ---- real batched: fftpack.c:14086 (rfftmi_), :14035 (rfftmf_), :13984 (rfftmb_); exported, not in fftpack.h ---- */
+int rfftmi_(int *n, fft_real_t *wsave, int *lensav, int *ier);
+int rfftmf_(int *lot, int *jump, int *n, int *inc, fft_real_t *r, int *lenr, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+int rfftmb_(int *lot, int *jump, int *n, int *inc, fft_real_t *r, int *lenr, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+
+/* ---- DCT-I (cost), DST-I (sint), quarter-wave cosine (cosq = DCT-III/II) and sine (sinq):
+ *      cfftpack/fftpack.h:112-147, 160-168; fftpack.c:6107/:6046/:5985 (cost1i_/f_/b_), :6551/:6485/:6419 (costm*),
+ *      :14667/:14611/:14553 (sint1*), :15066/:14999/:14931 (sintm*), :5523/:5448/:5374 (cosq1*),
+ *      :5931/:5845/:5750 (cosqm*), :14123-14513 (sinq1*, sinqm*) ---- */
+#define CFB200_DECL_TRIG(name)                                                                                        \
+  int name##1i_(int *n, fft_real_t *wsave, int *lensav, int *ier);                                                    \
+  int name##1f_(int *n, int *inc, fft_real_t *x, int *lenx, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier); \
+  int name##1b_(int *n, int *inc, fft_real_t *x, int *lenx, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier); \
+  int name##mi_(int *n, fft_real_t *wsave, int *lensav, int *ier);                                                    \
+  int name##mf_(int *lot, int *jump, int *n, int *inc, fft_real_t *x, int *lenx, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier); \
+  int name##mb_(int *lot, int *jump, int *n, int *inc, fft_real_t *x, int *lenx, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+CFB200_DECL_TRIG(cost)
+CFB200_DECL_TRIG(sint)
+CFB200_DECL_TRIG(cosq)
+CFB200_DECL_TRIG(sinq)
+
+/* ---- extensions (no counterpart in the reference) ---- */
+/* CUDA stream (cudaStream_t) used by THIS host thread for device-pointer calls; NULL = default stream */
+int cfb200_set_stream(void *cuda_stream);
+/* block until the calling thread's stream is idle; returns 0 or -1 */
+int cfb200_synchronize(void);
+/* number of kernels this library has launched since it was loaded (all threads) */
+unsigned long long cfb200_launch_count(void);
+/* message of the last failure on this thread ("" if none) */
+const char *cfb200_last_error(void);
+/* free cached device plans and scratch buffers */
+void cfb200_release(void);
+/* "cfftpack_b200 <version> sm_100a" */
+const char *cfb200_version(void);
+/* longest complex / real-family sequence that a single CTA transforms on chip */
+int cfb200_max_onchip_complex(void);
+int cfb200_max_onchip_real(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

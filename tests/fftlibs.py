@@ -41,7 +41,24 @@ def naive_ref():
 
 
 def product():
-    return _load(os.path.join(ROOT, "cfftpack_b200", "libcfftpack_b200.so"))
+    lib = _load(os.path.join(ROOT, "cfftpack_b200", "libcfftpack_b200.so"))
+    if lib is not None:
+        lib.cfb200_last_error.restype = ctypes.c_char_p
+        lib.cfb200_launch_count.restype = ctypes.c_ulonglong
+    return lib
+
+
+def sim():
+    """product sources compiled against the CUDA-thread emulator (tools/sim) -- CPU-side tests only"""
+    return _load(os.path.join(ROOT, "tools", "sim", "libcfftpack_sim.so"))
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
 
 
 def P(a):

@@ -1,0 +1,268 @@
+"""GPU parity tests: libcfftpack_b200.so, called through its C ABI, against the CPU oracle, the golden
+vectors produced by the unmodified reference, and size-independent properties at BASELINE.json's sizes.
+
+Bar (north_star): relative L2 error per sequence <= 1e-12 * log2(N)  (fl.tol).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import fftlibs as fl
+
+pytestmark = pytest.mark.gpu
+
+PROD = fl.Lib(fl.product())
+ORC = fl.Lib(fl.oracle(), "orc_")
+G = fl.golden()
+
+SIZES = [2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 20, 25, 27, 30, 32, 35, 49, 60, 64, 77, 100, 121, 128, 169, 210, 256,
+         343, 360, 500, 512, 625, 999, 1000, 1001, 1002, 1024, 2048, 4096]
+
+
+def _rows(a, lot, jump, n, inc):
+    return [a[m * jump + inc * np.arange(n)] for m in range(lot)]
+
+
+def _check_batched(fam, d, lot, jump, n, inc, seed=0, extra=0.0):
+    span = (lot - 1) * jump + (n - 1) * inc + 1
+    x = fl.rand_input(fam, span + 2, seed + 13 * n + lot)
+    a, ia = PROD.runm(fam, d, lot, jump, n, inc, x, lenx=span, work=False)
+    b, ib = ORC.runm(fam, d, lot, jump, n, inc, x, lenx=span)
+    assert ia == ib == 0, (fam, d, lot, jump, n, inc, ia, ib, fl.product().cfb200_last_error())
+    touched = np.zeros(len(x), bool)
+    for m in range(lot):
+        touched[m * jump + inc * np.arange(n)] = True
+    assert np.array_equal(a[~touched], x[~touched]), "elements outside the sequences must not change"
+    worst = max(fl.rel_l2(ra, rb) for ra, rb in zip(_rows(a, lot, jump, n, inc), _rows(b, lot, jump, n, inc)))
+    assert worst <= fl.tol(n) + extra, (fam, d, lot, jump, n, inc, worst)
+    return worst
+
+
+@pytest.mark.parametrize("fam", fl.FAMILIES)
+def test_single_sequence_vs_oracle(fam):
+    launches0 = fl.product().cfb200_launch_count()
+    for n in SIZES:
+        x = fl.rand_input(fam, n, 17 * n + 3)
+        for d in "fb":
+            a, ia = PROD.run1(fam, d, n, x)
+            b, ib = ORC.run1(fam, d, n, x)
+            assert ia == ib == 0, (fam, d, n, ia, ib, fl.product().cfb200_last_error())
+            assert fl.rel_l2(a, b) <= fl.tol(n), (fam, d, n, fl.rel_l2(a, b))
+    assert fl.product().cfb200_launch_count() > launches0, "no kernel was launched: the CUDA path did not run"
+
+
+@pytest.mark.parametrize("fam", fl.FAMILIES)
+def test_golden_vectors_from_the_reference(fam):
+    """outputs of the unmodified reference (tests/golden/make_golden.py), incl. its tests' own input vectors"""
+    for key in G.files:
+        if key.endswith("/y") and key.split("_")[0] == fam and key.count("_") == 3:
+            _, d, n, kind = key[:-2].split("_")
+            n = int(n)
+            if n == 1:
+                continue
+            y, ier = PROD.run1(fam, d, n, fl.vec(fam, kind, n))
+            assert ier == 0
+            e = fl.rel_l2(y, G[key])
+            assert e <= fl.tol(n) + fl.ref_noise(fam, n), (key, e)
+
+
+def test_golden_batched_and_2d():
+    for key in G.files:
+        if not key.endswith("/y"):
+            continue
+        name = key[:-2]
+        if name.startswith("cfft2_"):
+            d = name.split("_")[1]
+            ldim = 11 if name.endswith("ld11") else 8
+            y, ier = PROD.run2(d, ldim, 8, 6, G[name + "/x"])
+            assert ier == 0 and fl.rel_l2(y, G[key]) <= fl.tol(48), name
+        elif name[4:6] == "m_":
+            fam, d = name[:4], name[6]
+            lot, n = (int(v) for v in name.split("_")[2].split("x"))
+            jump, inc = (n, 1) if name.endswith("cols") else (1, lot)
+            y, ier = PROD.runm(fam, d, lot, jump, n, inc, G[name + "/x"], work=False)
+            assert ier == 0 and fl.rel_l2(y, G[key]) <= fl.tol(n), name
+
+
+@pytest.mark.parametrize("fam", fl.FAMILIES)
+def test_lot_jump_inc_layouts(fam):
+    for (lot, n) in ((5, 12), (33, 64), (7, 30), (17, 128), (64, 100), (3, 1024), (40, 256)):
+        for d in "fb":
+            _check_batched(fam, d, lot, n, n, 1)
+            _check_batched(fam, d, lot, 1, n, lot)
+            _check_batched(fam, d, lot, n + 3, n, 1)
+            _check_batched(fam, d, lot, 1, n, lot + 2)
+            _check_batched(fam, d, lot, 2 * n + 1, n, 2)
+
+
+def test_config4_dct_dst_lengths():
+    """cost/sint/cosq at N = 1000 and 1001 (underlying real FFTs 999, 1000, 1001, 1002 -- SURVEY 8(a) note 2)"""
+    for fam in ("cost", "sint", "cosq", "sinq"):
+        for n in (1000, 1001):
+            for d in "fb":
+                _check_batched(fam, d, 65, n, n, 1, seed=5)
+                _check_batched(fam, d, 16, 1, n, 16, seed=6)
+
+
+def test_headline_shapes_reduced_lot():
+    for fam in ("cfft", "rfft"):
+        for d in "fb":
+            _check_batched(fam, d, 33, 4096, 4096, 1)
+            _check_batched(fam, d, 8, 1, 4096, 8)
+            _check_batched(fam, d, 5, 8192, 8192, 1)
+
+
+def test_long_complex_four_step():
+    nmax = fl.product().cfb200_max_onchip_complex()
+    for n in (16384, 7 * 11 * 13 * 9, 2 * nmax + 2, 65536):
+        for d in "fb":
+            _check_batched("cfft", d, 3, n, n, 1)
+    _check_batched("cfft", "f", 4, 1, 16384, 4)
+
+
+def test_cfft2_vs_oracle():
+    for (ldim, l, m) in ((8, 8, 6), (11, 8, 6), (64, 64, 64), (130, 128, 96), (1024, 1024, 512), (100, 100, 75)):
+        c = fl.rand_input("cfft", ldim * m, l + m)
+        for d in "fb":
+            a, ia = PROD.run2(d, ldim, l, m, c)
+            b, ib = ORC.run2(d, ldim, l, m, c)
+            assert ia == ib == 0
+            assert fl.rel_l2(a, b) <= fl.tol(l * m), (d, ldim, l, m, fl.rel_l2(a, b))
+
+
+def test_known_answers():
+    """impulse, constant and single tone under the reference's scaling (forward 1/N e^{-i}, backward e^{+i})"""
+    n = 4096
+    x = np.zeros(n, np.complex128)
+    x[1] = 1.0
+    y, _ = PROD.run1("cfft", "f", n, x)
+    k = np.arange(n)
+    assert np.max(np.abs(y - np.exp(-2j * np.pi * k / n) / n)) < 1e-15
+    y, _ = PROD.run1("cfft", "b", n, x)
+    assert np.max(np.abs(y - np.exp(2j * np.pi * k / n))) < 1e-12
+    y, _ = PROD.run1("cfft", "f", n, np.ones(n, np.complex128))
+    assert abs(y[0] - 1) < 1e-15 and np.max(np.abs(y[1:])) < 1e-15
+    # real tone: x_t = cos(2 pi 3 t/n) + 0.5 sin(2 pi 5 t/n)  ->  a_3 = 1, b_5 = 0.5 (rfftmf_ convention)
+    t = np.arange(n)
+    r, _ = PROD.run1("rfft", "f", n, np.cos(2 * np.pi * 3 * t / n) + 0.5 * np.sin(2 * np.pi * 5 * t / n))
+    want = np.zeros(n)
+    want[2 * 3 - 1] = 1.0
+    want[2 * 5] = 0.5
+    assert np.max(np.abs(r - want)) < 1e-14
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def test_device_pointers_full_size_config2_properties():
+    """BASELINE config 2: cfftmf_ N=4096, lot=65536 on device-resident data: forward then backward is the identity,
+    a sample of sequences agrees with the oracle, and the library really launched kernels."""
+    torch = _torch()
+    import cfftpack_b200 as cb
+    n, lot = 4096, 65536
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand(lot * n, 2, generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    x0 = x.clone()
+    plan = cb.Plan("cfft", n)
+    before = cb.launch_count()
+    assert plan.multi("f", x.data_ptr(), lot, n, 1, lot * n) == 0
+    cb.synchronize()
+    sample = [0, 1, 777, 32768, 65535]
+    want_in = np.stack([torch.view_as_complex(x0[i * n:(i + 1) * n]).cpu().numpy() for i in sample]).ravel()
+    want, ier = ORC.runm("cfft", "f", len(sample), n, n, 1, want_in)
+    got = np.stack([torch.view_as_complex(x[i * n:(i + 1) * n]).cpu().numpy() for i in sample]).ravel()
+    for j in range(len(sample)):
+        assert fl.rel_l2(got[j * n:(j + 1) * n], want[j * n:(j + 1) * n]) <= fl.tol(n)
+    assert plan.multi("b", x.data_ptr(), lot, n, 1, lot * n) == 0
+    cb.synchronize()
+    assert cb.launch_count() >= before + 2
+    err = (x - x0).norm() / x0.norm()
+    assert float(err) <= fl.tol(n), float(err)
+    # Parseval on the whole batch (checksum of checksums): sum |X|^2 * N == sum |x|^2
+    assert plan.multi("f", x.data_ptr(), lot, n, 1, lot * n) == 0
+    cb.synchronize()
+    e_in, e_out = float((x0 * x0).sum()), float((x * x).sum()) * n
+    assert abs(e_in - e_out) <= 1e-11 * e_in
+
+
+def test_device_pointers_full_size_config3_properties():
+    """BASELINE config 3: rfftmf_ N=4096, lot=65536."""
+    torch = _torch()
+    import cfftpack_b200 as cb
+    n, lot = 4096, 65536
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand(lot * n, generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    x0 = x.clone()
+    plan = cb.Plan("rfft", n)
+    assert plan.multi("f", x.data_ptr(), lot, n, 1, lot * n) == 0
+    cb.synchronize()
+    sample = [0, 1, 4097, 65534, 65535]
+    want_in = np.concatenate([x0[i * n:(i + 1) * n].cpu().numpy() for i in sample])
+    want, ier = ORC.runm("rfft", "f", len(sample), n, n, 1, want_in)
+    got = np.concatenate([x[i * n:(i + 1) * n].cpu().numpy() for i in sample])
+    for j in range(len(sample)):
+        assert fl.rel_l2(got[j * n:(j + 1) * n], want[j * n:(j + 1) * n]) <= fl.tol(n)
+    assert plan.multi("b", x.data_ptr(), lot, n, 1, lot * n) == 0
+    cb.synchronize()
+    err = (x - x0).norm() / x0.norm()
+    assert float(err) <= fl.tol(n), float(err)
+
+
+def test_device_pointers_config4_roundtrip_and_sample():
+    torch = _torch()
+    import cfftpack_b200 as cb
+    lot = 32768
+    for fam, n in (("cost", 1001), ("sint", 1000), ("cosq", 1000), ("cosq", 1001), ("cost", 1000), ("sint", 1001)):
+        g = torch.Generator(device="cuda").manual_seed(n)
+        x = torch.rand(lot * n, generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+        x0 = x.clone()
+        plan = cb.Plan(fam, n)
+        assert plan.multi("f", x.data_ptr(), lot, n, 1, lot * n) == 0, cb.last_error()
+        cb.synchronize()
+        sample = [0, 1, 12345, 32767]
+        want_in = np.concatenate([x0[i * n:(i + 1) * n].cpu().numpy() for i in sample])
+        want, ier = ORC.runm(fam, "f", len(sample), n, n, 1, want_in)
+        got = np.concatenate([x[i * n:(i + 1) * n].cpu().numpy() for i in sample])
+        for j in range(len(sample)):
+            assert fl.rel_l2(got[j * n:(j + 1) * n], want[j * n:(j + 1) * n]) <= fl.tol(n), (fam, n)
+        assert plan.multi("b", x.data_ptr(), lot, n, 1, lot * n) == 0
+        cb.synchronize()
+        err = float((x - x0).norm() / x0.norm())
+        assert err <= fl.tol(n), (fam, n, err)
+
+
+def test_cfft2_16384_device_roundtrip_and_separability():
+    """BASELINE config 5 shape on one GPU: 2-D forward of a separable input equals the outer product of 1-D
+    transforms; forward then backward is the identity."""
+    torch = _torch()
+    import cfftpack_b200 as cb
+    l = m = 16384
+    g = torch.Generator(device="cuda").manual_seed(3)
+    u = torch.view_as_complex(torch.rand(l, 2, generator=g, device="cuda", dtype=torch.float64) - 0.5)
+    v = torch.view_as_complex(torch.rand(m, 2, generator=g, device="cuda", dtype=torch.float64) - 0.5)
+    c = (v[:, None] * u[None, :]).contiguous()  # column-major c(l, m): c[j, i] = u[i] v[j]
+    lib = fl.product()
+    ws, ls, ier = PROD.init2(l, m)
+    I = ctypes.c_int
+    ierc = I(-1)
+    dummy = ctypes.c_double(0)
+    args = (ctypes.byref(I(l)), ctypes.byref(I(l)), ctypes.byref(I(m)), ctypes.c_void_p(c.data_ptr()), fl.P(ws),
+            ctypes.byref(I(ls)), ctypes.byref(dummy), ctypes.byref(I(2 * l * m)), ctypes.byref(ierc))
+    lib.cfft2f_(*args)
+    cb.synchronize()
+    assert ierc.value == 0, lib.cfb200_last_error()
+    U, _ = ORC.run1("cfft", "f", l, u.cpu().numpy())
+    V, _ = ORC.run1("cfft", "f", m, v.cpu().numpy())
+    rows = [0, 1, 5000, 16383]
+    for j in rows:
+        got = c[j].cpu().numpy()
+        assert fl.rel_l2(got, V[j] * U) <= fl.tol(l * m), j
+    lib.cfft2b_(*args)
+    cb.synchronize()
+    assert ierc.value == 0
+    back = (v[:, None] * u[None, :])
+    err = float((torch.view_as_real(c) - torch.view_as_real(back)).norm() / torch.view_as_real(back).norm())
+    assert err <= fl.tol(l * m), err

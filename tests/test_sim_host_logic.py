@@ -1,0 +1,103 @@
+"""Host logic + kernel index arithmetic on the CPU: the product's own sources compiled against the
+CUDA-thread emulator (tools/sim), compared with the oracle.  This is how plans, launch geometry, the
+lot/jump/inc handling, the pair packing of real sequences and the four-step split are tested where no GPU
+exists.  The emulator is test infrastructure; libcfftpack_b200.so neither contains nor loads it.
+"""
+import subprocess
+import os
+
+import numpy as np
+import pytest
+
+import fftlibs as fl
+
+
+@pytest.fixture(scope="module")
+def libs():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(fl.ROOT, "tools", "sim")])
+    fl._cache.pop(os.path.join(fl.ROOT, "tools", "sim", "libcfftpack_sim.so"), None)
+    return fl.Lib(fl.sim()), fl.Lib(fl.oracle(), "orc_")
+
+
+def _check(S, O, fam, d, lot, jump, n, inc, seed=0):
+    span = (lot - 1) * jump + (n - 1) * inc + 1
+    x = fl.rand_input(fam, span + 3, seed + 13 * n + lot)
+    a, ia = S.runm(fam, d, lot, jump, n, inc, x, lenx=span)
+    b, ib = O.runm(fam, d, lot, jump, n, inc, x, lenx=span)
+    assert ia == ib == 0, (fam, d, lot, jump, n, inc, ia, ib)
+    # untouched elements must stay bit-identical; touched ones within the parity bar
+    touched = np.zeros(len(x), bool)
+    for m in range(lot):
+        touched[m * jump + inc * np.arange(n)] = True
+    assert np.array_equal(a[~touched], x[~touched])
+    for m in range(lot):
+        idx = m * jump + inc * np.arange(n)
+        e = fl.rel_l2(a[idx], b[idx])
+        assert e <= fl.tol(n), (fam, d, lot, jump, n, inc, m, e)
+
+
+@pytest.mark.parametrize("fam", fl.FAMILIES)
+def test_single_sequence_sizes(libs, fam):
+    S, O = libs
+    for n in [2, 3, 4, 5, 6, 7, 8, 9, 11, 12, 16, 27, 30, 32, 35, 49, 60, 64, 100, 128, 210, 256]:
+        x = fl.rand_input(fam, n, 17 * n + 3)
+        for d in "fb":
+            a, ia = S.run1(fam, d, n, x)
+            b, ib = O.run1(fam, d, n, x)
+            assert ia == ib == 0
+            assert fl.rel_l2(a, b) <= fl.tol(n), (fam, d, n)
+
+
+@pytest.mark.parametrize("fam", fl.FAMILIES)
+def test_lot_jump_inc_layouts(libs, fam):
+    S, O = libs
+    for (lot, n) in ((5, 12), (4, 64), (7, 30), (3, 128), (9, 8)):
+        for d in "fb":
+            _check(S, O, fam, d, lot, n, n, 1)          # contiguous sequences (test/ftest.c:42-47)
+            _check(S, O, fam, d, lot, 1, n, lot)        # interleaved (test/ftest.c:64), cfft2f_'s first sweep
+            _check(S, O, fam, d, lot, n + 3, n, 1)      # padded rows
+            _check(S, O, fam, d, lot, 1, n, lot + 2)    # padded interleave
+            _check(S, O, fam, d, lot, 2 * n + 1, n, 2)  # both strides non-unit
+
+
+def test_config4_lengths(libs):
+    S, O = libs
+    for fam, n in (("cost", 1001), ("sint", 1000), ("cosq", 1000), ("cosq", 1001), ("cost", 1000), ("sint", 1001)):
+        for d in "fb":
+            _check(S, O, fam, d, 3, n, n, 1, seed=5)
+
+
+def test_headline_lengths(libs):
+    S, O = libs
+    for fam in ("cfft", "rfft"):
+        for d in "fb":
+            _check(S, O, fam, d, 3, 4096, 4096, 1)
+            _check(S, O, fam, d, 2, 1024, 1024, 1)
+            _check(S, O, fam, d, 2, 1, 4096, 2)  # same length through the strided engine
+
+
+def test_four_step_long_complex(libs):
+    S, O = libs
+    nmax = fl.sim().cfb200_max_onchip_complex()
+    for n in (8192 * 2, 7 * 11 * 13 * 9, 2 * nmax + 2):
+        if n <= nmax:
+            continue
+        for d in "fb":
+            _check(S, O, "cfft", d, 2, n, n, 1)
+    _check(S, O, "cfft", "f", 2, 1, 8192, 2)  # interleaved long: pow2 kernel not applicable -> four-step
+
+
+def test_cfft2(libs):
+    S, O = libs
+    for (ldim, l, m) in ((8, 8, 6), (11, 8, 6), (64, 64, 64), (130, 128, 96)):
+        c = fl.rand_input("cfft", ldim * m, l + m)
+        for d in "fb":
+            a, ia = S.run2(d, ldim, l, m, c)
+            b, ib = O.run2(d, ldim, l, m, c)
+            assert ia == ib == 0
+            assert fl.rel_l2(a, b) <= fl.tol(l * m), (d, ldim, l, m)
+            if ldim > l:
+                pad = np.ones(ldim * m, bool)
+                for j in range(m):
+                    pad[j * ldim: j * ldim + l] = False
+                assert np.array_equal(a[pad], c[pad])
