@@ -1,7 +1,10 @@
 /* pow2.cu -- host side of the power-of-two register kernels: twiddle tables, attributes, launches. */
 #include "pow2.cuh"
 
+#include <stdlib.h>
+
 #include <map>
+#include <tuple>
 #include <vector>
 
 #include "plan.h"
@@ -10,28 +13,37 @@ namespace cfb {
 
 namespace {
 std::mutex g_mu;
-std::map<std::pair<int, int>, cpx *> g_tw;  // (device, log2n) -> table
+std::map<std::tuple<int, int, int, int>, cpx *> g_tw;  // (device, log2n, lp, tw) -> table
 
-template <int LOG2N>
+template <class C>
 const cpx *pow2_table() {
-  typedef Pow2Cfg<LOG2N> C;
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lk(g_mu);
-  auto key = std::make_pair(dev, LOG2N);
+  int l2 = 0;
+  while ((1 << l2) < C::N) ++l2;
+  auto key = std::make_tuple(dev, l2, C::LP, C::TW);
   auto it = g_tw.find(key);
   if (it != g_tw.end()) return it->second;
   std::vector<cpx> h((size_t)C::TW_COUNT + 1);
   size_t o = 0;
   for (int st = 0; st < C::NFULL; ++st) {
-    const int m = C::N >> (C::LP * (st + 1));
+    if (C::stage_last(st)) break;
+    const int m = C::stage_m(st);
     const long long ncur = (long long)m * C::P;
-    if (st == C::NFULL - 1 && C::REM == 0) break;
-    for (int k = 1; k < C::P; ++k)
-      for (int p = 0; p < m; ++p) {
-        unit_root((long long)p * k, ncur, &h[o].x, &h[o].y);
-        ++o;
-      }
+    if (C::stage_computed(st)) {
+      for (int e = 1; e <= 4; e += 3)  // w^p then w^(4p)
+        for (int p = 0; p < m; ++p) {
+          unit_root((long long)p * e, ncur, &h[o].x, &h[o].y);
+          ++o;
+        }
+    } else {
+      for (int k = 1; k < C::P; ++k)
+        for (int p = 0; p < m; ++p) {
+          unit_root((long long)p * k, ncur, &h[o].x, &h[o].y);
+          ++o;
+        }
+    }
   }
   cpx *d = nullptr;
   if (!cuda_ok(cudaMalloc((void **)&d, h.size() * sizeof(cpx)), "cudaMalloc(pow2 twiddles)")) return nullptr;
@@ -46,21 +58,22 @@ const cpx *pow2_table() {
 template <class K>
 bool set_smem_once(K kernel, size_t smem, std::once_flag &once, bool &ok) {
   std::call_once(once, [&] {
-    ok = smem <= 48 * 1024 ||
-         cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                 "cudaFuncSetAttribute(pow2 kernel)");
+    ok = cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                 "cudaFuncSetAttribute(pow2 kernel, smem size)") &&
+         // ask for the full shared-memory carveout: three 68 KiB CTAs only fit next to a minimal L1
+         cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
+                 "cudaFuncSetAttribute(pow2 kernel, carveout)");
   });
   return ok;
 }
 
-template <int LOG2N, int DIR>
-bool launch_c2c(long long lot, long long jump, cpx *c) {
-  typedef Pow2Cfg<LOG2N> C;
-  const cpx *tw = pow2_table<LOG2N>();
+template <class C, int MINB, int DIR>
+bool launch_c2c_cfg(long long lot, long long jump, cpx *c) {
+  const cpx *tw = pow2_table<C>();
   if (!tw) return false;
   static std::once_flag once;
   static bool ok = true;
-  auto kern = pow2_c2c_kernel<LOG2N, DIR>;
+  auto kern = pow2_c2c_kernel<C, MINB, DIR>;
   if (!set_smem_once(kern, C::SMEM, once, ok)) return false;
   const long long grid = (lot + C::TPB - 1) / C::TPB;
   const double scale = DIR < 0 ? 1.0 / (double)C::N : 1.0;
@@ -69,20 +82,92 @@ bool launch_c2c(long long lot, long long jump, cpx *c) {
   return cuda_ok(cudaGetLastError(), "pow2_c2c_kernel launch");
 }
 
-template <int LOG2N, int DIR>
-bool launch_r2c(long long lot, long long jump, double *r) {
-  typedef Pow2Cfg<LOG2N> C;
-  const cpx *tw = pow2_table<LOG2N>();
+template <class C, int MINB, int DIR>
+bool launch_r2c_cfg(long long lot, long long jump, double *r) {
+  const cpx *tw = pow2_table<C>();
   if (!tw) return false;
   static std::once_flag once;
   static bool ok = true;
-  auto kern = pow2_r2c_kernel<LOG2N, DIR>;
+  auto kern = pow2_r2c_kernel<C, MINB, DIR>;
   if (!set_smem_once(kern, C::SMEM, once, ok)) return false;
   const long long pairs = (lot + 1) / 2;
   const long long grid = (pairs + C::TPB - 1) / C::TPB;
   CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, C::SMEM, current_stream(), r, lot, jump, tw);
   count_launch();
   return cuda_ok(cudaGetLastError(), "pow2_r2c_kernel launch");
+}
+
+template <class C, int MINB, int DIR>
+bool launch_c2c_stream(long long lot, long long jump, cpx *c) {
+  const cpx *tw = pow2_table<C>();
+  if (!tw) return false;
+  static std::once_flag once;
+  static bool ok = true;
+  auto kern = pow2_c2c_stream_kernel<C, MINB, DIR>;
+  if (!set_smem_once(kern, StreamSmem<C>::BYTES, once, ok)) return false;
+  const long long ntiles = (lot + C::TPB - 1) / C::TPB;
+  const long long cap = (long long)MINB * sm_count();
+  const long long grid = ntiles < cap ? ntiles : cap;
+  const double scale = DIR < 0 ? 1.0 / (double)C::N : 1.0;
+  CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, StreamSmem<C>::BYTES, current_stream(), c, lot, jump, tw, scale, ntiles);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "pow2_c2c_stream_kernel launch");
+}
+
+template <class C, int MINB, int DIR>
+bool launch_r2c_stream(long long lot, long long jump, double *r) {
+  const cpx *tw = pow2_table<C>();
+  if (!tw) return false;
+  static std::once_flag once;
+  static bool ok = true;
+  auto kern = pow2_r2c_stream_kernel<C, MINB, DIR>;
+  if (!set_smem_once(kern, StreamSmem<C>::BYTES, once, ok)) return false;
+  const long long pairs = (lot + 1) / 2;
+  const long long ntiles = (pairs + C::TPB - 1) / C::TPB;
+  const long long cap = (long long)MINB * sm_count();
+  const long long grid = ntiles < cap ? ntiles : cap;
+  CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, StreamSmem<C>::BYTES, current_stream(), r, lot, jump, tw, ntiles);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "pow2_r2c_stream_kernel launch");
+}
+
+/* tuning knob for experiments (N = 4096 only): CFB200_POW2_VARIANT, see DESIGN.md */
+int variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CFB200_POW2_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <int LOG2N>
+struct StreamMinB {
+  static constexpr int value = LOG2N >= 13 ? 1 : (Pow2Cfg<LOG2N>::LP == 3 ? 4 : 2);
+};
+
+template <int LOG2N, int DIR>
+bool launch_c2c(long long lot, long long jump, cpx *c) {
+  if (LOG2N == 12) {
+    switch (variant()) {
+      case 1: return launch_c2c_cfg<Pow2Cfg<12, 4, 0>, 2, DIR>(lot, jump, c);  // direct loads, table twiddles, 2 CTAs/SM
+      case 2: return launch_c2c_cfg<Pow2Cfg<12, 4, 1>, 2, DIR>(lot, jump, c);  // direct loads, rebuilt twiddles
+      case 3: return launch_c2c_cfg<Pow2Cfg<12, 4, 1>, 3, DIR>(lot, jump, c);  // ... 3 CTAs/SM (spills)
+      case 4: return launch_c2c_cfg<Pow2Cfg<12, 3, 1>, 2, DIR>(lot, jump, c);  // 8 points/thread, 512 threads
+      case 6: return launch_c2c_stream<Pow2Cfg<12, 3, 1>, 2, DIR>(lot, jump, c);  // streaming, 8 points/thread
+      case 7: return launch_c2c_stream<Pow2Cfg<12, 4, 0>, 2, DIR>(lot, jump, c);  // streaming, table twiddles
+      default: break;
+    }
+  }
+  return launch_c2c_stream<Pow2Cfg<LOG2N>, StreamMinB<LOG2N>::value, DIR>(lot, jump, c);
+}
+template <int LOG2N, int DIR>
+bool launch_r2c(long long lot, long long jump, double *r) {
+  // the bulk-copy engine needs 16-byte aligned rows: odd jumps (or an odd base) take the direct-load kernel
+  const bool tma_ok = (jump % 2 == 0) && (((uintptr_t)r & 15) == 0);
+  if (!tma_ok || (LOG2N == 12 && variant() == 1))
+    return launch_r2c_cfg<Pow2Cfg<LOG2N>, (LOG2N >= 13 ? 1 : 2), DIR>(lot, jump, r);
+  return launch_r2c_stream<Pow2Cfg<LOG2N>, StreamMinB<LOG2N>::value, DIR>(lot, jump, r);
 }
 
 int ilog2_exact(int n) {

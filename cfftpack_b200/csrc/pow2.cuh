@@ -21,13 +21,17 @@
 
 #include "butterfly.cuh"
 #include "internal.h"
+#include "tma.cuh"
 
 namespace cfb {
 
-template <int LOG2N>
+/* LP = log2(points per thread); TW = 1: the twiddles of a stage with many distinct values are rebuilt in
+ * registers from two table entries (w^p, w^4p) instead of P-1 loads (keeps the tables L1-resident) */
+template <int LOG2N, int LP_ = ((LOG2N >= 8) ? 4 : 3), int TW_ = 1>
 struct Pow2Cfg {
   static constexpr int N = 1 << LOG2N;
-  static constexpr int LP = (LOG2N >= 8) ? 4 : 3;  // log2 of points per thread
+  static constexpr int LP = LP_;
+  static constexpr int TW = TW_;
   static constexpr int P = 1 << LP;
   static constexpr int NT = N / P;                 // threads per sequence
   static constexpr int THREADS = (NT > 256) ? NT : 256;
@@ -36,14 +40,54 @@ struct Pow2Cfg {
   static constexpr int REM = LOG2N % LP;
   static constexpr int TILE = N + (N >> LP);       // padded elements per sequence
   static constexpr size_t SMEM = (size_t)TPB * TILE * sizeof(cpx);
-  // twiddle table: for full stage st (not last): (P-1) * m_st entries laid out [k-1][p]
+  static constexpr int stage_m(int st) { return N >> (LP * (st + 1)); }
+  static constexpr bool stage_last(int st) { return st == NFULL - 1 && REM == 0; }
+  static constexpr bool stage_computed(int st) { return TW == 1 && stage_m(st) >= 64; }
+  // table entries of stage st: 2*m (w^p, w^4p) when rebuilt in registers, else (P-1)*m laid out [k-1][p]
+  static constexpr int stage_count(int st) {
+    return stage_last(st) ? 0 : stage_computed(st) ? 2 * stage_m(st) : (P - 1) * stage_m(st);
+  }
   static constexpr int tw_offset(int st) {
     int off = 0;
-    for (int i = 0; i < st; ++i) off += (P - 1) * (N >> (LP * (i + 1)));
+    for (int i = 0; i < st; ++i) off += stage_count(i);
     return off;
   }
   static constexpr int TW_COUNT = tw_offset(NFULL);
 };
+
+/* a[k] *= w^k (k = 1..P-1) with w^2, w^3, ... formed from w1 = w and w4 = w^4 (at most three products deep) */
+template <int DIR>
+__device__ __forceinline__ void twiddle_powers(cpx (&a)[8], cpx w1, cpx w4) {
+  cpx w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+  a[1] = ctw<DIR>(a[1], w1);
+  a[2] = ctw<DIR>(a[2], w2);
+  a[3] = ctw<DIR>(a[3], w3);
+  a[4] = ctw<DIR>(a[4], w4);
+  a[5] = ctw<DIR>(a[5], cmul(w4, w1));
+  a[6] = ctw<DIR>(a[6], cmul(w4, w2));
+  a[7] = ctw<DIR>(a[7], cmul(w4, w3));
+}
+template <int DIR>
+__device__ __forceinline__ void twiddle_powers(cpx (&a)[16], cpx w1, cpx w4) {
+  cpx w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+  a[1] = ctw<DIR>(a[1], w1);
+  a[2] = ctw<DIR>(a[2], w2);
+  a[3] = ctw<DIR>(a[3], w3);
+  a[4] = ctw<DIR>(a[4], w4);
+  a[5] = ctw<DIR>(a[5], cmul(w4, w1));
+  a[6] = ctw<DIR>(a[6], cmul(w4, w2));
+  a[7] = ctw<DIR>(a[7], cmul(w4, w3));
+  cpx w8 = cmul(w4, w4);
+  a[8] = ctw<DIR>(a[8], w8);
+  a[9] = ctw<DIR>(a[9], cmul(w8, w1));
+  a[10] = ctw<DIR>(a[10], cmul(w8, w2));
+  a[11] = ctw<DIR>(a[11], cmul(w8, w3));
+  cpx w12 = cmul(w8, w4);
+  a[12] = ctw<DIR>(a[12], w12);
+  a[13] = ctw<DIR>(a[13], cmul(w12, w1));
+  a[14] = ctw<DIR>(a[14], cmul(w12, w2));
+  a[15] = ctw<DIR>(a[15], cmul(w12, w3));
+}
 
 template <int LP>
 __device__ __forceinline__ int pad(int e) {
@@ -51,10 +95,9 @@ __device__ __forceinline__ int pad(int e) {
 }
 
 /* all stages of one length-N transform; a[i] <-> element t + NT*i on entry and on exit (natural order) */
-template <int LOG2N, int DIR>
-__device__ __forceinline__ void pow2_core(cpx (&a)[Pow2Cfg<LOG2N>::P], cpx *__restrict__ sm, const int t,
+template <class C, int DIR>
+__device__ __forceinline__ void pow2_core(cpx (&a)[C::P], cpx *__restrict__ sm, const int t,
                                           const cpx *__restrict__ tw) {
-  typedef Pow2Cfg<LOG2N> C;
   constexpr int P = C::P, LP = C::LP, NT = C::NT;
 #pragma unroll
   for (int st = 0; st < C::NFULL; ++st) {
@@ -65,7 +108,9 @@ __device__ __forceinline__ void pow2_core(cpx (&a)[Pow2Cfg<LOG2N>::P], cpx *__re
     if (!last) {
       const int p = t >> (LP * st), q = t & (s - 1);
       const cpx *twp = tw + C::tw_offset(st) + p;
-      if (m > 1) {
+      if (C::stage_computed(st)) {
+        twiddle_powers<DIR>(a, __ldg(twp), __ldg(twp + m));
+      } else if (m > 1) {
 #pragma unroll
         for (int k = 1; k < P; ++k) a[k] = ctw<DIR>(a[k], __ldg(twp + (k - 1) * m));
       }
@@ -92,11 +137,9 @@ __device__ __forceinline__ void pow2_core(cpx (&a)[Pow2Cfg<LOG2N>::P], cpx *__re
   }
 }
 
-template <int LOG2N, int DIR>
-__global__ void __launch_bounds__(Pow2Cfg<LOG2N>::THREADS) pow2_c2c_kernel(cpx *__restrict__ c, long long lot,
-                                                                             long long jump,
-                                                                             const cpx *__restrict__ tw, double scale) {
-  typedef Pow2Cfg<LOG2N> C;
+template <class C, int MINB, int DIR>
+__global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_kernel(cpx *__restrict__ c, long long lot, long long jump,
+                                                                    const cpx *__restrict__ tw, double scale) {
   CFB_DYN_SMEM(smem_raw);
   const int tl = threadIdx.x / C::NT, t = threadIdx.x % C::NT;
   const long long g = (long long)blockIdx.x * C::TPB + tl;
@@ -106,7 +149,7 @@ __global__ void __launch_bounds__(Pow2Cfg<LOG2N>::THREADS) pow2_c2c_kernel(cpx *
   cpx a[C::P];
 #pragma unroll
   for (int i = 0; i < C::P; ++i) a[i] = live ? x[C::NT * i] : make_double2(0.0, 0.0);
-  pow2_core<LOG2N, DIR>(a, sm, t, tw);
+  pow2_core<C, DIR>(a, sm, t, tw);
   if (live) {
 #pragma unroll
     for (int i = 0; i < C::P; ++i) x[C::NT * i] = make_double2(a[i].x * scale, a[i].y * scale);
@@ -115,11 +158,9 @@ __global__ void __launch_bounds__(Pow2Cfg<LOG2N>::THREADS) pow2_c2c_kernel(cpx *
 
 /* two real sequences per complex transform.  DIR = -1: rfftmf_ (x -> scaled half-complex, fftpack.c:10281-10349),
  * DIR = +1: rfftmb_ (half-complex -> x). */
-template <int LOG2N, int DIR>
-__global__ void __launch_bounds__(Pow2Cfg<LOG2N>::THREADS) pow2_r2c_kernel(double *__restrict__ r, long long lot,
-                                                                             long long jump,
-                                                                             const cpx *__restrict__ tw) {
-  typedef Pow2Cfg<LOG2N> C;
+template <class C, int MINB, int DIR>
+__global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_kernel(double *__restrict__ r, long long lot, long long jump,
+                                                                    const cpx *__restrict__ tw) {
   constexpr int N = C::N, P = C::P, NT = C::NT, LP = C::LP;
   CFB_DYN_SMEM(smem_raw);
   const int tl = threadIdx.x / NT, t = threadIdx.x % NT;
@@ -132,7 +173,7 @@ __global__ void __launch_bounds__(Pow2Cfg<LOG2N>::THREADS) pow2_r2c_kernel(doubl
   if (DIR < 0) {
 #pragma unroll
     for (int i = 0; i < P; ++i) a[i] = make_double2(la ? xa[t + NT * i] : 0.0, lb ? xb[t + NT * i] : 0.0);
-    pow2_core<LOG2N, DIR>(a, sm, t, tw);
+    pow2_core<C, DIR>(a, sm, t, tw);
     // separate X_a, X_b: needs Z[N-f]; the upper half of the registers goes through shared memory
 #pragma unroll
     for (int i = P / 2; i < P; ++i) sm[pad<LP>(t + NT * i)] = a[i];
@@ -181,11 +222,210 @@ __global__ void __launch_bounds__(Pow2Cfg<LOG2N>::THREADS) pow2_r2c_kernel(doubl
 #pragma unroll
     for (int i = P / 2; i < P; ++i) a[i] = sm[pad<LP>(t + NT * i)];
     __syncthreads();
-    pow2_core<LOG2N, DIR>(a, sm, t, tw);
+    pow2_core<C, DIR>(a, sm, t, tw);
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       if (la) xa[t + NT * i] = a[i].x;
       if (lb) xb[t + NT * i] = a[i].y;
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Streaming variants.  A persistent CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the next tile is
+ * brought into a shared-memory landing buffer by the bulk-copy engine (TMA, one cp.async.bulk per sequence)
+ * while the current one is being transformed, so HBM reads never wait for registers or for the butterflies.
+ * To make room for the landing buffer the exchange tile holds one double per element: real and imaginary
+ * parts are exchanged in two rounds through the same 8-byte padded tile.
+ * --------------------------------------------------------------------------------------------------------- */
+template <class C>
+struct StreamSmem {
+  static constexpr size_t LAND = (size_t)C::TPB * C::N * sizeof(cpx);
+  static constexpr size_t XCH = (size_t)C::TPB * C::TILE * sizeof(double);
+  static constexpr size_t BYTES = LAND + XCH + 16;
+};
+
+template <class C, int DIR>
+__device__ __forceinline__ void pow2_core_split(cpx (&a)[C::P], double *__restrict__ xr, const int t,
+                                                const cpx *__restrict__ tw) {
+  constexpr int P = C::P, LP = C::LP, NT = C::NT;
+#pragma unroll
+  for (int st = 0; st < C::NFULL; ++st) {
+    const int s = 1 << (LP * st);
+    const int m = C::N >> (LP * (st + 1));
+    const bool last = (st == C::NFULL - 1) && (C::REM == 0);
+    Dft<P, DIR>::run(a);
+    if (!last) {
+      const int p = t >> (LP * st), q = t & (s - 1);
+      const cpx *twp = tw + C::tw_offset(st) + p;
+      if (C::stage_computed(st)) {
+        twiddle_powers<DIR>(a, __ldg(twp), __ldg(twp + m));
+      } else if (m > 1) {
+#pragma unroll
+        for (int k = 1; k < P; ++k) a[k] = ctw<DIR>(a[k], __ldg(twp + (k - 1) * m));
+      }
+      const int base = q + s * P * p;
+#pragma unroll
+      for (int k = 0; k < P; ++k) xr[pad<LP>(base + s * k)] = a[k].x;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < P; ++i) a[i].x = xr[pad<LP>(t + NT * i)];
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < P; ++k) xr[pad<LP>(base + s * k)] = a[k].y;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < P; ++i) a[i].y = xr[pad<LP>(t + NT * i)];
+      __syncthreads();
+    }
+  }
+  if (C::REM > 0) {
+    constexpr int R = 1 << (C::REM > 0 ? C::REM : 1), G = P / R;
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      cpx b[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) b[j] = a[u + G * j];
+      Dft<R, DIR>::run(b);
+#pragma unroll
+      for (int j = 0; j < R; ++j) a[u + G * j] = b[j];
+    }
+  }
+}
+
+/* thread 0: arm the barrier and start the bulk copies of one tile (TPB sequences of `bytes` each) */
+template <int TPB>
+__device__ __forceinline__ void stream_issue(char *land, const char *gbase, long long lot, long long jump_bytes,
+                                             long long tile, unsigned seq_bytes, uint64_t *bar) {
+  const long long g0 = tile * TPB;
+  const int live = (int)((lot - g0) < TPB ? (lot - g0) : TPB);
+  mbar_expect_tx(bar, (unsigned)live * seq_bytes);
+  for (int i = 0; i < live; ++i) bulk_g2s(land + (size_t)i * seq_bytes, gbase + (g0 + i) * jump_bytes, seq_bytes, bar);
+}
+
+template <class C, int MINB, int DIR>
+__global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_stream_kernel(cpx *__restrict__ c, long long lot,
+                                                                           long long jump, const cpx *__restrict__ tw,
+                                                                           double scale, long long ntiles) {
+  CFB_DYN_SMEM(smem_raw);
+  constexpr int N = C::N, P = C::P, NT = C::NT;
+  cpx *land = (cpx *)smem_raw;
+  double *xch = (double *)(smem_raw + StreamSmem<C>::LAND);
+  uint64_t *bar = (uint64_t *)(smem_raw + StreamSmem<C>::LAND + StreamSmem<C>::XCH);
+  const int tid = threadIdx.x, tl = tid / NT, t = tid % NT;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, tile, N * 16, bar);
+  unsigned parity = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const long long g = tile * C::TPB + tl;
+    const bool live = g < lot;
+    cpx a[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) a[i] = land[(size_t)tl * N + t + NT * i];
+    __syncthreads();  // the landing buffer has been consumed: refill it with the next tile while we compute
+    const long long next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
+    pow2_core_split<C, DIR>(a, xch + (size_t)tl * C::TILE, t, tw);
+    if (live) {
+      cpx *x = c + g * jump + t;
+#pragma unroll
+      for (int i = 0; i < P; ++i) x[NT * i] = make_double2(a[i].x * scale, a[i].y * scale);
+    }
+  }
+}
+
+/* real pairs, streaming: the landing buffer holds the two rows x_a, x_b of each pair back to back */
+template <class C, int MINB, int DIR>
+__global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(double *__restrict__ r, long long lot,
+                                                                           long long jump, const cpx *__restrict__ tw,
+                                                                           long long ntiles) {
+  CFB_DYN_SMEM(smem_raw);
+  constexpr int N = C::N, P = C::P, NT = C::NT;
+  double *land = (double *)smem_raw;  // [TPB][2][N]
+  double *xch = (double *)(smem_raw + StreamSmem<C>::LAND);
+  uint64_t *bar = (uint64_t *)(smem_raw + StreamSmem<C>::LAND + StreamSmem<C>::XCH);
+  const int tid = threadIdx.x, tl = tid / NT, t = tid % NT;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  // a tile = TPB pairs = 2*TPB consecutive sequences; reuse stream_issue with a "sequence" = one real row
+  constexpr int ROWS = 2 * C::TPB;
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, tile, N * 8, bar);
+  unsigned parity = 0;
+  const double *la = land + (size_t)(2 * tl) * N, *lb = la + N;
+  double *xq = xch + (size_t)tl * C::TILE;
+  for (; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const long long ga = 2 * (tile * C::TPB + tl), gb = ga + 1;
+    const bool va = ga < lot, vb = gb < lot;
+    double *xa = r + (va ? ga : 0) * jump, *xb = r + (vb ? gb : 0) * jump;
+    cpx a[P];
+    if (DIR < 0) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) a[i] = make_double2(la[t + NT * i], vb ? lb[t + NT * i] : 0.0);
+    } else {
+      // Z[e] from the half-complex rows (rfftb1_ convention): e < N/2: (a1 + b2, b1 - a2); e > N/2 uses f = N - e
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        const int e = t + NT * i;
+        if (e == 0) a[i] = make_double2(la[0], vb ? lb[0] : 0.0);
+        else if (e == N / 2) a[i] = make_double2(la[N - 1], vb ? lb[N - 1] : 0.0);
+        else {
+          const int f = e < N / 2 ? e : N - e;
+          double a1 = 0.5 * la[2 * f - 1], a2 = 0.5 * la[2 * f];
+          double b1 = vb ? 0.5 * lb[2 * f - 1] : 0.0, b2 = vb ? 0.5 * lb[2 * f] : 0.0;
+          a[i] = e < N / 2 ? make_double2(a1 + b2, b1 - a2) : make_double2(a1 - b2, b1 + a2);
+        }
+      }
+    }
+    __syncthreads();
+    const long long next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
+    pow2_core_split<C, DIR>(a, xq, t, tw);
+    if (DIR < 0) {
+      // separate X_a, X_b: Z[N-f] of the upper half goes through the exchange tile, viewed as N/2 complex slots
+      cpx *zq = (cpx *)xq;
+#pragma unroll
+      for (int i = P / 2; i < P; ++i) zq[t + NT * (i - P / 2)] = a[i];
+      __syncthreads();
+      const double sc = 1.0 / (double)N;
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        const int f = t + NT * i;
+        if (f == 0) {
+          cpx v = zq[0];
+          if (va) {
+            xa[0] = a[0].x * sc;
+            xa[N - 1] = v.x * sc;
+          }
+          if (vb) {
+            xb[0] = a[0].y * sc;
+            xb[N - 1] = v.y * sc;
+          }
+        } else {
+          cpx u = a[i], v = zq[N / 2 - f];
+          if (va) {
+            xa[2 * f - 1] = (u.x + v.x) * sc;
+            xa[2 * f] = (v.y - u.y) * sc;
+          }
+          if (vb) {
+            xb[2 * f - 1] = (u.y + v.y) * sc;
+            xb[2 * f] = (u.x - v.x) * sc;
+          }
+        }
+      }
+      __syncthreads();  // zq is reused by the next tile's first exchange
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        if (va) xa[t + NT * i] = a[i].x;
+        if (vb) xb[t + NT * i] = a[i].y;
+      }
     }
   }
 }

@@ -1,0 +1,63 @@
+/*
+ * tma.cuh -- the bulk-asynchronous copy engine (TMA, cp.async.bulk) and mbarrier primitives used to stream
+ * whole sequences from HBM into shared memory without staging through registers.  sm_90+ PTX; in SASS these
+ * appear as UBLKCP / SYNCS (B200_PROFILING.md).  Under -DCFB_SIM (CPU tests) the copy is a memcpy and the
+ * barrier is a no-op, because the emulator runs the issuing thread's copy to completion at once.
+ */
+#ifndef CFB_TMA_CUH
+#define CFB_TMA_CUH
+#include "cfb_rt.h"
+
+namespace cfb {
+
+#ifdef CFB_SIM
+/* emulated transaction barrier: low word = completed phases, high word = bytes still expected */
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) { *bar += (uint64_t)bytes << 32; }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  while (((unsigned)(*bar) & 1u) == parity) cfbsim::yield_once();
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+  if ((((uintptr_t)smem_dst) | ((uintptr_t)gsrc) | bytes) & 15) {
+    fprintf(stderr, "cfbsim: cp.async.bulk needs 16-byte aligned addresses and size (%p <- %p, %u)\n", smem_dst, gsrc, bytes);
+    abort();
+  }
+  memcpy(smem_dst, gsrc, bytes);
+  *bar -= (uint64_t)bytes << 32;
+  if ((*bar >> 32) == 0) *bar += 1;  // all bytes of this phase have landed
+}
+#else
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+/* one arrival + the number of bytes the bulk copies of this phase will deliver */
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+/* global -> shared bulk copy; bytes and both addresses are multiples of 16; completion is signalled on bar */
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+#endif
+
+}  // namespace cfb
+#endif

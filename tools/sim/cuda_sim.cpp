@@ -32,6 +32,8 @@ void trampoline() {
 void yield() { swapcontext(&fibers[running].uc, &sched_uc); }
 }  // namespace
 
+void yield_once() { yield(); }
+
 void yield_barrier() {
   Fiber &f = fibers[running];
   f.bar_gen++;

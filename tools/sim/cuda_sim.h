@@ -56,6 +56,7 @@ extern Ctx *cur;              // context of the running fiber
 extern char *dyn_smem;        // dynamic shared memory of the running block
 void yield_barrier();         // __syncthreads
 void warp_barrier();          // internal, for shuffles
+void yield_once();            // let the other fibers run (spin-wait emulation)
 double shfl(double v, int src_lane);
 void run(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
 }  // namespace cfbsim
@@ -99,7 +100,7 @@ struct cudaPointerAttributes {
   cudaMemoryType type;
   int device;
 };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 static inline const char *cudaGetErrorString(cudaError_t) { return "sim"; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaMalloc(void **p, size_t n) {
