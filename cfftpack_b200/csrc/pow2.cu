@@ -55,6 +55,40 @@ const cpx *pow2_table() {
   return d;
 }
 
+/* streaming kernels: per non-last stage the rows w^p and w^(4p) (copied to shared memory by each CTA) */
+template <class C>
+const cpx *pow2_stream_table() {
+  typedef StreamSmem<C> S;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  int l2 = 0;
+  while ((1 << l2) < C::N) ++l2;
+  auto key = std::make_tuple(dev, l2, C::LP, 100);
+  auto it = g_tw.find(key);
+  if (it != g_tw.end()) return it->second;
+  std::vector<cpx> h((size_t)S::TWS_COUNT + 1);
+  size_t o = 0;
+  for (int st = 0; st < C::NFULL; ++st) {
+    if (C::stage_last(st)) continue;
+    const int m = C::stage_m(st);
+    const long long ncur = (long long)m * C::P;
+    for (int e = 1; e <= 4; e += 3)
+      for (int p = 0; p < m; ++p) {
+        unit_root((long long)p * e, ncur, &h[o].x, &h[o].y);
+        ++o;
+      }
+  }
+  cpx *d = nullptr;
+  if (!cuda_ok(cudaMalloc((void **)&d, h.size() * sizeof(cpx)), "cudaMalloc(pow2 twiddles)")) return nullptr;
+  if (!cuda_ok(cudaMemcpy(d, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy(pow2 twiddles)")) {
+    cudaFree(d);
+    return nullptr;
+  }
+  g_tw[key] = d;
+  return d;
+}
+
 template <class K>
 bool set_smem_once(K kernel, size_t smem, std::once_flag &once, bool &ok) {
   std::call_once(once, [&] {
@@ -99,7 +133,7 @@ bool launch_r2c_cfg(long long lot, long long jump, double *r) {
 
 template <class C, int MINB, int DIR>
 bool launch_c2c_stream(long long lot, long long jump, cpx *c) {
-  const cpx *tw = pow2_table<C>();
+  const cpx *tw = pow2_stream_table<C>();
   if (!tw) return false;
   static std::once_flag once;
   static bool ok = true;
@@ -116,7 +150,7 @@ bool launch_c2c_stream(long long lot, long long jump, cpx *c) {
 
 template <class C, int MINB, int DIR>
 bool launch_r2c_stream(long long lot, long long jump, double *r) {
-  const cpx *tw = pow2_table<C>();
+  const cpx *tw = pow2_stream_table<C>();
   if (!tw) return false;
   static std::once_flag once;
   static bool ok = true;
@@ -155,7 +189,6 @@ bool launch_c2c(long long lot, long long jump, cpx *c) {
       case 3: return launch_c2c_cfg<Pow2Cfg<12, 4, 1>, 3, DIR>(lot, jump, c);  // ... 3 CTAs/SM (spills)
       case 4: return launch_c2c_cfg<Pow2Cfg<12, 3, 1>, 2, DIR>(lot, jump, c);  // 8 points/thread, 512 threads
       case 6: return launch_c2c_stream<Pow2Cfg<12, 3, 1>, 2, DIR>(lot, jump, c);  // streaming, 8 points/thread
-      case 7: return launch_c2c_stream<Pow2Cfg<12, 4, 0>, 2, DIR>(lot, jump, c);  // streaming, table twiddles
       default: break;
     }
   }

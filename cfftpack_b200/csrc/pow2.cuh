@@ -240,15 +240,31 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_kernel(double *__re
  * --------------------------------------------------------------------------------------------------------- */
 template <class C>
 struct StreamSmem {
+  static constexpr int PADW = (C::LP == 4) ? 2 : 1;  // doubles of padding per P elements
+  static constexpr int XTILE = C::N + PADW * (C::N >> C::LP);
+  // twiddles of the streaming kernels: per non-last stage the two rows w^p and w^(4p), p < m, kept in shared memory
+  static constexpr int tws_offset(int st) {
+    int off = 0;
+    for (int i = 0; i < st; ++i) off += C::stage_last(i) ? 0 : 2 * C::stage_m(i);
+    return off;
+  }
+  static constexpr int TWS_COUNT = tws_offset(C::NFULL);
   static constexpr size_t LAND = (size_t)C::TPB * C::N * sizeof(cpx);
-  static constexpr size_t XCH = (size_t)C::TPB * C::TILE * sizeof(double);
-  static constexpr size_t BYTES = LAND + XCH + 16;
+  static constexpr size_t XCH = (size_t)C::TPB * XTILE * sizeof(double);
+  static constexpr size_t TWS = (size_t)(TWS_COUNT > 0 ? TWS_COUNT : 1) * sizeof(cpx);
+  static constexpr size_t BYTES = LAND + XCH + TWS + 16;
 };
+
+template <class C>
+__device__ __forceinline__ int xpad(int e) {
+  return e + StreamSmem<C>::PADW * (e >> C::LP);
+}
 
 template <class C, int DIR>
 __device__ __forceinline__ void pow2_core_split(cpx (&a)[C::P], double *__restrict__ xr, const int t,
-                                                const cpx *__restrict__ tw) {
+                                                const cpx *__restrict__ tws) {
   constexpr int P = C::P, LP = C::LP, NT = C::NT;
+  typedef StreamSmem<C> S;
 #pragma unroll
   for (int st = 0; st < C::NFULL; ++st) {
     const int s = 1 << (LP * st);
@@ -257,25 +273,33 @@ __device__ __forceinline__ void pow2_core_split(cpx (&a)[C::P], double *__restri
     Dft<P, DIR>::run(a);
     if (!last) {
       const int p = t >> (LP * st), q = t & (s - 1);
-      const cpx *twp = tw + C::tw_offset(st) + p;
-      if (C::stage_computed(st)) {
-        twiddle_powers<DIR>(a, __ldg(twp), __ldg(twp + m));
-      } else if (m > 1) {
-#pragma unroll
-        for (int k = 1; k < P; ++k) a[k] = ctw<DIR>(a[k], __ldg(twp + (k - 1) * m));
-      }
+      const cpx *twp = tws + S::tws_offset(st) + p;
+      twiddle_powers<DIR>(a, twp[0], twp[m]);
       const int base = q + s * P * p;
+      if (st == 0 && S::PADW == 2) {
+        // first exchange: a thread's P outputs are adjacent -> 16-byte stores (row pitch P+2 keeps them aligned)
+        double2 *row = (double2 *)(xr + xpad<C>(base));
 #pragma unroll
-      for (int k = 0; k < P; ++k) xr[pad<LP>(base + s * k)] = a[k].x;
+        for (int k = 0; k < P; k += 2) row[k / 2] = make_double2(a[k].x, a[k + 1].x);
+      } else {
+#pragma unroll
+        for (int k = 0; k < P; ++k) xr[xpad<C>(base + s * k)] = a[k].x;
+      }
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < P; ++i) a[i].x = xr[pad<LP>(t + NT * i)];
+      for (int i = 0; i < P; ++i) a[i].x = xr[xpad<C>(t + NT * i)];
+      __syncthreads();
+      if (st == 0 && S::PADW == 2) {
+        double2 *row = (double2 *)(xr + xpad<C>(base));
+#pragma unroll
+        for (int k = 0; k < P; k += 2) row[k / 2] = make_double2(a[k].y, a[k + 1].y);
+      } else {
+#pragma unroll
+        for (int k = 0; k < P; ++k) xr[xpad<C>(base + s * k)] = a[k].y;
+      }
       __syncthreads();
 #pragma unroll
-      for (int k = 0; k < P; ++k) xr[pad<LP>(base + s * k)] = a[k].y;
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < P; ++i) a[i].y = xr[pad<LP>(t + NT * i)];
+      for (int i = 0; i < P; ++i) a[i].y = xr[xpad<C>(t + NT * i)];
       __syncthreads();
     }
   }
@@ -309,11 +333,14 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_stream_kernel(cpx *
                                                                            double scale, long long ntiles) {
   CFB_DYN_SMEM(smem_raw);
   constexpr int N = C::N, P = C::P, NT = C::NT;
+  typedef StreamSmem<C> S;
   cpx *land = (cpx *)smem_raw;
-  double *xch = (double *)(smem_raw + StreamSmem<C>::LAND);
-  uint64_t *bar = (uint64_t *)(smem_raw + StreamSmem<C>::LAND + StreamSmem<C>::XCH);
+  double *xch = (double *)(smem_raw + S::LAND);
+  cpx *tws = (cpx *)(smem_raw + S::LAND + S::XCH);
+  uint64_t *bar = (uint64_t *)(smem_raw + S::LAND + S::XCH + S::TWS);
   const int tid = threadIdx.x, tl = tid / NT, t = tid % NT;
   if (tid == 0) mbar_init(bar, 1);
+  for (int i = tid; i < S::TWS_COUNT; i += C::THREADS) tws[i] = __ldg(tw + i);
   __syncthreads();
   long long tile = blockIdx.x;
   if (tid == 0 && tile < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, tile, N * 16, bar);
@@ -329,7 +356,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_stream_kernel(cpx *
     __syncthreads();  // the landing buffer has been consumed: refill it with the next tile while we compute
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
-    pow2_core_split<C, DIR>(a, xch + (size_t)tl * C::TILE, t, tw);
+    pow2_core_split<C, DIR>(a, xch + (size_t)tl * S::XTILE, t, tws);
     if (live) {
       cpx *x = c + g * jump + t;
 #pragma unroll
@@ -345,11 +372,14 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
                                                                            long long ntiles) {
   CFB_DYN_SMEM(smem_raw);
   constexpr int N = C::N, P = C::P, NT = C::NT;
+  typedef StreamSmem<C> S;
   double *land = (double *)smem_raw;  // [TPB][2][N]
-  double *xch = (double *)(smem_raw + StreamSmem<C>::LAND);
-  uint64_t *bar = (uint64_t *)(smem_raw + StreamSmem<C>::LAND + StreamSmem<C>::XCH);
+  double *xch = (double *)(smem_raw + S::LAND);
+  cpx *tws = (cpx *)(smem_raw + S::LAND + S::XCH);
+  uint64_t *bar = (uint64_t *)(smem_raw + S::LAND + S::XCH + S::TWS);
   const int tid = threadIdx.x, tl = tid / NT, t = tid % NT;
   if (tid == 0) mbar_init(bar, 1);
+  for (int i = tid; i < S::TWS_COUNT; i += C::THREADS) tws[i] = __ldg(tw + i);
   __syncthreads();
   // a tile = TPB pairs = 2*TPB consecutive sequences; reuse stream_issue with a "sequence" = one real row
   constexpr int ROWS = 2 * C::TPB;
@@ -357,7 +387,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
   if (tid == 0 && tile < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, tile, N * 8, bar);
   unsigned parity = 0;
   const double *la = land + (size_t)(2 * tl) * N, *lb = la + N;
-  double *xq = xch + (size_t)tl * C::TILE;
+  double *xq = xch + (size_t)tl * S::XTILE;
   for (; tile < ntiles; tile += gridDim.x) {
     mbar_wait(bar, parity);
     parity ^= 1;
@@ -386,7 +416,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
     __syncthreads();
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
-    pow2_core_split<C, DIR>(a, xq, t, tw);
+    pow2_core_split<C, DIR>(a, xq, t, tws);
     if (DIR < 0) {
       // separate X_a, X_b: Z[N-f] of the upper half goes through the exchange tile, viewed as N/2 complex slots
       cpx *zq = (cpx *)xq;

@@ -26,6 +26,9 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
   *bar -= (uint64_t)bytes << 32;
   if ((*bar >> 32) == 0) *bar += 1;  // all bytes of this phase have landed
 }
+__device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+  bulk_g2s(smem_dst, gsrc, bytes, bar);
+}
 #else
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -56,6 +59,16 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+/* same, tagging the lines evict-first in L2: a streamed sequence is read exactly once */
+__device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
 }
 #endif
 
