@@ -423,30 +423,42 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
 #pragma unroll
       for (int i = P / 2; i < P; ++i) zq[t + NT * (i - P / 2)] = a[i];
       __syncthreads();
+      // FFTPACK's half-complex row is [X0, A1, B1, A2, B2, ..., A_{N/2}] with A_f = 2 Re X_f / N, B_f = -2 Im X_f / N
+      // (rfftf1_ epilogue, fftpack.c:13818-13853).  16-byte aligned pairs are (B_f, A_{f+1}): A_{f+1} comes from the
+      // next lane by shuffle, so that all but the warp-edge lanes issue full 16-byte stores.
       const double sc = 1.0 / (double)N;
+      const int lane = tid & 31;
 #pragma unroll
       for (int i = 0; i < P / 2; ++i) {
         const int f = t + NT * i;
-        if (f == 0) {
-          cpx v = zq[0];
-          if (va) {
-            xa[0] = a[0].x * sc;
-            xa[N - 1] = v.x * sc;
-          }
-          if (vb) {
-            xb[0] = a[0].y * sc;
-            xb[N - 1] = v.y * sc;
-          }
+        cpx u = a[i], v = zq[f == 0 ? 0 : N / 2 - f];
+        double Aa, Ba, Ab, Bb;
+        if (f == 0) {  // slot 0 holds X0 itself
+          Aa = 0.0;
+          Ab = 0.0;
+          Ba = u.x * sc;
+          Bb = u.y * sc;
         } else {
-          cpx u = a[i], v = zq[N / 2 - f];
-          if (va) {
-            xa[2 * f - 1] = (u.x + v.x) * sc;
-            xa[2 * f] = (v.y - u.y) * sc;
-          }
-          if (vb) {
-            xb[2 * f - 1] = (u.y + v.y) * sc;
-            xb[2 * f] = (u.x - v.x) * sc;
-          }
+          Aa = (u.x + v.x) * sc;
+          Ba = (v.y - u.y) * sc;
+          Ab = (u.y + v.y) * sc;
+          Bb = (u.x - v.x) * sc;
+        }
+        const double Aa_n = __shfl_down_sync(0xffffffffu, Aa, 1), Ab_n = __shfl_down_sync(0xffffffffu, Ab, 1);
+        if (lane < 31 && t != NT - 1) {
+          if (va) *(double2 *)(xa + 2 * f) = make_double2(Ba, Aa_n);
+          if (vb) *(double2 *)(xb + 2 * f) = make_double2(Bb, Ab_n);
+        } else {
+          if (va) xa[2 * f] = Ba;
+          if (vb) xb[2 * f] = Bb;
+        }
+        if ((lane == 0 || t == 0) && f != 0) {
+          if (va) xa[2 * f - 1] = Aa;
+          if (vb) xb[2 * f - 1] = Ab;
+        }
+        if (f == 0) {  // A_{N/2} = X_{N/2} / N closes the row
+          if (va) xa[N - 1] = v.x * sc;
+          if (vb) xb[N - 1] = v.y * sc;
         }
       }
       __syncthreads();  // zq is reused by the next tile's first exchange
