@@ -303,7 +303,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": f"pow2_{'c2c' if fam == 'cfft' else 'r2c'}_kernel<{int(math.log2(n))},-1>",
+                "traffic": traffic, "peak_source": peak_src, "kernel": f"pow2_{'c2c' if fam == 'cfft' else 'r2c'}_stream_kernel<Pow2Cfg<{int(math.log2(n))}>, DIR=-1>",
                 "algorithmic_bytes_per_launch": bytes_rank, "avg_launch_ms": avg_ms, "median_launch_ms": kern_ms,
                 "frac_of_8TBps_nominal": achieved / 8000.0}
 

@@ -22,7 +22,7 @@ static const size_t SMEM_MAX = 227 * 1024;      // opt-in limit per CTA on sm_10
 static const size_t SMEM_TARGET = 72 * 1024;    // aim: three CTAs per SM for the streaming kernels
 
 int engine_max_c2c() { return (int)((SMEM_MAX - 1024) / 32) - 2; }
-int engine_max_real() { return (int)((SMEM_MAX - 2048) / 48) - 4; }
+int engine_max_real() { return (int)((SMEM_MAX - 1024) / 32) - 4; }
 
 static bool engine_attr_once() {
   static std::once_flag once;
@@ -52,15 +52,22 @@ static Addr make_addr(long long inc, long long jump_lo, long long jump_hi, long 
   return a;
 }
 
+static int log2_ceil_capped(long long v, int cap) {
+  int l = 0;
+  while ((1LL << l) < v && l < cap) ++l;
+  return l;
+}
+
 /* one engine launch; P has kind/dir/n/addresses/plan filled in */
 static bool launch_engine(EngineParams &P) {
   if (!engine_attr_once()) return false;
   const bool real = P.kind != K_C2C;
-  P.ldz = P.M | 1;
-  P.ldx = (P.n + 1) | 1;
-  const size_t per = real ? (size_t)P.ldz * 32 + (size_t)P.ldx * 16 + 16 : (size_t)P.ldz * 32;
+  const int len = real ? P.n : P.M;  // elements per row that cross the global-memory boundary
+  P.ldz = (P.M > P.n ? P.M : P.n) | 1;
+  P.ldx = 0;
+  const size_t per = (size_t)P.ldz * 32 + (real ? 64 : 32);  // per sequence (c2c) or per pair (real kinds)
   const long long units = real ? (P.lot + 1) / 2 : P.lot;
-  if (per > SMEM_MAX) {
+  if (per + 64 > SMEM_MAX) {
     set_error("length %d does not fit one CTA (%zu bytes)", P.n, per);
     return false;
   }
@@ -68,13 +75,16 @@ static bool launch_engine(EngineParams &P) {
   const bool strided = P.ain.lanes_t || P.aout.lanes_t;
   // batch-contiguous layouts want at least 8 sequences side by side (128-byte runs of 16-byte elements)
   const long long want = strided ? (real ? 4 : 8) : 1;
-  if (T < want) T = (long long)(SMEM_MAX / per) < want ? (long long)(SMEM_MAX / per) : want;
+  if (T < want) T = (long long)((SMEM_MAX - 64) / per) < want ? (long long)((SMEM_MAX - 64) / per) : want;
   if (T < 1) T = 1;
   if (T > 32) T = 32;
   if (T > units) T = units;
-  // two-level batches: keep a tile inside one group when that costs nothing
   P.T = (int)T;
-  const size_t smem = per * (size_t)T;
+  const long long rows = real ? 2 * T : T;
+  // thread tiling of the loader/storer: threads along the contiguous axis first
+  P.tx_in_log2 = log2_ceil_capped(P.ain.lanes_t ? rows : len, 8);
+  P.tx_out_log2 = log2_ceil_capped(P.aout.lanes_t ? rows : len, 8);
+  const size_t smem = per * (size_t)T + 64;
   const long long grid = (units + T - 1) / T;
   if (grid > 2147483647LL) {
     set_error("batch too large");

@@ -27,6 +27,8 @@
 namespace cfb {
 
 /* ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ int fast_div(int n, int d, unsigned mag) { return d == 1 ? n : (int)__umulhi((unsigned)n, mag); }
+
 /* one radix-R pass over T sequences: src, dst are [T][ldz] complex arrays in shared memory       */
 template <int R, int DIR>
 __device__ __forceinline__ void pass_fixed(const cpx *__restrict__ src, cpx *__restrict__ dst, int T, int ldz, int M,
@@ -36,14 +38,14 @@ __device__ __forceinline__ void pass_fixed(const cpx *__restrict__ src, cpx *__r
   const int s = pd.s, m = pd.m;
   const cpx *twp = tw + pd.twoff;
   for (int idx = tid; idx < total; idx += nthr) {
-    int t = idx / nb, b = idx - t * nb;
-    int p = b / s, q = b - p * s;
+    int t = fast_div(idx, nb, pd.mag_nb), b = idx - t * nb;
+    int p = fast_div(b, s, pd.mag_s), q = b - p * s;
     cpx a[R];
-    const cpx *sp = src + (size_t)t * ldz + b;
+    const cpx *sp = src + t * ldz + b;
 #pragma unroll
     for (int j = 0; j < R; ++j) a[j] = sp[j * nb];
     Dft<R, DIR>::run(a);
-    cpx *dp = dst + (size_t)t * ldz + q + (size_t)s * R * p;
+    cpx *dp = dst + t * ldz + q + s * R * p;
     dp[0] = a[0];
     if (m > 1) {
 #pragma unroll
@@ -66,11 +68,11 @@ __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *_
   const cpx *twp = tw + pd.twoff;
   const cpx *rt = tw + pd.rtoff;
   for (int idx = tid; idx < total; idx += nthr) {
-    int t = idx / per, rem = idx - t * per;
-    int k = rem / nb, b = rem - k * nb;
-    int p = b / s, q = b - p * s;
-    const cpx *sp = src + (size_t)t * ldz + b;
-    cpx *dp = dst + (size_t)t * ldz + q + (size_t)s * r * p;
+    int t = fast_div(idx, per, pd.mag_per), rem = idx - t * per;
+    int k = fast_div(rem, nb, pd.mag_nb), b = rem - k * nb;
+    int p = fast_div(b, s, pd.mag_s), q = b - p * s;
+    const cpx *sp = src + t * ldz + b;
+    cpx *dp = dst + t * ldz + q + s * r * p;
     cpx a0 = sp[0];
     if (k == 0) {
       cpx acc = a0;
@@ -104,8 +106,8 @@ __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *_
         xk = ctw<DIR>(xk, __ldg(twp + (k - 1) * m + p));
         xc = ctw<DIR>(xc, __ldg(twp + (r - k - 1) * m + p));
       }
-      dp[(size_t)k * s] = xk;
-      dp[(size_t)(r - k) * s] = xc;
+      dp[k * s] = xk;
+      dp[(r - k) * s] = xc;
     }
   }
 }
@@ -120,7 +122,6 @@ __device__ __forceinline__ void run_passes(cpx *&cur, cpx *&oth, const EnginePar
       case 4: pass_fixed<4, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
       case 5: pass_fixed<5, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
       case 8: pass_fixed<8, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
-      case 16: pass_fixed<16, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
       default: pass_generic<DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
     }
     __syncthreads();
@@ -353,147 +354,171 @@ __device__ __forceinline__ void post_sequence(int kind, int dir, int n, int M, c
 }
 
 /* ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(CFB_ENGINE_THREADS) engine_kernel(const EngineParams P) {
+/* loader / storer tiling: 2^txl threads walk the axis that is contiguous in global memory (elements when
+ * lanes_t == 0, rows when lanes_t == 1), the remaining threads walk the other axis.  No divisions. */
+#define CFB_TILE_LOOP(ROWS, LEN, LANES_T, TXL, BODY)                                   \
+  {                                                                                    \
+    const int tx_ = tid & ((1 << (TXL)) - 1), ty_ = tid >> (TXL);                      \
+    const int nx_ = 1 << (TXL), ny_ = nthr >> (TXL);                                   \
+    if (LANES_T) {                                                                     \
+      for (int e = ty_; e < (LEN); e += ny_)                                           \
+        for (int r = tx_; r < (ROWS); r += nx_) BODY                                   \
+    } else {                                                                           \
+      for (int r = ty_; r < (ROWS); r += ny_)                                          \
+        for (int e = tx_; e < (LEN); e += nx_) BODY                                    \
+    }                                                                                  \
+  }
+
+__global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const EngineParams P) {
   CFB_DYN_SMEM(smem_raw);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int T = P.T, ldz = P.ldz, M = P.M, n = P.n;
   cpx *zA = (cpx *)smem_raw;
-  cpx *zB = zA + (size_t)T * ldz;
-  const long long g0 = (long long)blockIdx.x * T;
+  cpx *zB = zA + T * ldz;
+  const int rows = (P.kind == K_C2C) ? T : 2 * T;
+  long long *off_in = (long long *)(zB + T * ldz);  // [rows] element offsets of each row, -1 = past the batch
+  long long *off_out = off_in + rows;
+  double *dsum = (double *)(off_out + rows);         // [rows]
+  int *row_lo = (int *)(dsum + rows);                // [rows] index within the inner batch level (four-step twiddle)
+  const long long row0 = (long long)blockIdx.x * rows;
+  for (int r = tid; r < rows; r += nthr) {
+    long long g = row0 + r;
+    off_in[r] = g < P.lot ? batch_off(P.ain, g) : -1;
+    off_out[r] = g < P.lot ? batch_off(P.aout, g) : -1;
+    row_lo[r] = (int)(g % P.aout.nlo);
+  }
+  __syncthreads();
 
   if (P.kind == K_C2C) {
     /* ---- load: global -> zA ---- */
     const cpx *in = (const cpx *)P.in;
-    const int total = T * M;
-    for (int idx = tid; idx < total; idx += nthr) {
-      int t, e;
-      tile_index(idx, T, M, P.ain.lanes_t, t, e);
-      long long g = g0 + t;
+    const long long inc_in = P.ain.inc;
+    const int al = P.aligned16;
+    CFB_TILE_LOOP(T, M, P.ain.lanes_t, P.tx_in_log2, {
       cpx v = make_double2(0.0, 0.0);
-      if (g < P.lot) {
-        const cpx *p = in + batch_off(P.ain, g) + (long long)e * P.ain.inc;
-        if (P.aligned16) v = *p;
+      const long long o = off_in[r];
+      if (o >= 0) {
+        const cpx *p = in + o + e * inc_in;
+        if (al) v = *p;
         else {
           v.x = ((const double *)p)[0];
           v.y = ((const double *)p)[1];
         }
       }
-      zA[(size_t)t * ldz + e] = v;
-    }
+      zA[r * ldz + e] = v;
+    })
     __syncthreads();
     cpx *cur = zA, *oth = zB;
     if (P.dir < 0) run_passes<-1>(cur, oth, P, tid, nthr);
     else run_passes<1>(cur, oth, P, tid, nthr);
     /* ---- store: cur -> global ---- */
     cpx *out = (cpx *)P.out;
-    for (int idx = tid; idx < total; idx += nthr) {
-      int t, e;
-      tile_index(idx, T, M, P.aout.lanes_t, t, e);
-      long long g = g0 + t;
-      if (g >= P.lot) continue;
-      cpx v = cur[(size_t)t * ldz + e];
-      v.x *= P.scale;
-      v.y *= P.scale;
-      if (P.fs_tw) {
-        long long lo = g % P.aout.nlo;
-        cpx w = __ldg(P.fs_tw + (int)((lo * e) % P.fs_n));
-        v = (P.dir < 0) ? cmul(v, w) : cmulc(v, w);
+    const long long inc_out = P.aout.inc;
+    const double scale = P.scale;
+    const cpx *fs = P.fs_tw;
+    CFB_TILE_LOOP(T, M, P.aout.lanes_t, P.tx_out_log2, {
+      const long long o = off_out[r];
+      if (o >= 0) {
+        cpx v = cur[r * ldz + e];
+        v.x *= scale;
+        v.y *= scale;
+        if (fs) {  // W_n^(lo*e); lo < n2 and e < n1, so lo*e < n = fs_n: no reduction needed
+          cpx w = __ldg(fs + row_lo[r] * e);
+          v = (P.dir < 0) ? cmul(v, w) : cmulc(v, w);
+        }
+        cpx *p = out + o + e * inc_out;
+        if (al) *p = v;
+        else {
+          ((double *)p)[0] = v.x;
+          ((double *)p)[1] = v.y;
+        }
       }
-      cpx *p = out + batch_off(P.aout, g) + (long long)e * P.aout.inc;
-      if (P.aligned16) *p = v;
-      else {
-        ((double *)p)[0] = v.x;
-        ((double *)p)[1] = v.y;
-      }
-    }
+    })
     return;
   }
 
-  /* ---- real kinds: T pairs of sequences ---- */
-  const int ldx = P.ldx, rows = 2 * T;
-  double *xs = (double *)(zB + (size_t)T * ldz);  // [2T][ldx]
-  double *dsum = xs + (size_t)rows * ldx;          // [2T]
+  /* ---- real kinds: T pairs of sequences.  Real rows live in whichever complex buffer is free, viewed as
+   * [2T][ldz] doubles (exactly one complex buffer). ---- */
   const int kind = P.kind, dir = P.dir;
   const bool fwd_core = !((kind == K_RFFT || kind == K_COSQ || kind == K_SINQ) && dir > 0);
-  const long long s0 = 2 * g0;  // first sequence of this CTA
   const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+  double *rowsB = (double *)zB, *rowsA = (double *)zA;
   {
-    /* load: global -> xs.  sinq reverses the sequence (forward) or flips odd entries (backward),
+    /* load: global -> real rows in zB.  sinq reverses the sequence (forward) or flips odd entries (backward),
      * sinqf1_/sinqb1_ fftpack.c:14247-14266 */
     const double *in = (const double *)P.in;
-    const int total = rows * n;
-    for (int idx = tid; idx < total; idx += nthr) {
-      int r, e;
-      tile_index(idx, rows, n, P.ain.lanes_t, r, e);
-      long long g = s0 + r;
+    const long long inc_in = P.ain.inc;
+    CFB_TILE_LOOP(rows, n, P.ain.lanes_t, P.tx_in_log2, {
+      const long long o = off_in[r];
       double v = 0.0;
-      if (g < P.lot) v = in[batch_off(P.ain, g) + (long long)e * P.ain.inc];
+      if (o >= 0) v = in[o + e * inc_in];
       int ed = e;
       if (kind == K_SINQ) {
         if (dir < 0) ed = n - 1 - e;
         else if (e & 1) v = -v;
       }
-      xs[(size_t)r * ldx + ed] = v;
-    }
+      rowsB[r * ldz + ed] = v;
+    })
   }
   __syncthreads();
-  cpx *cur = zA, *oth = zB;
+  cpx *cur, *oth;
   if (fwd_core) {
     for (int r = warp; r < rows; r += nwarp)
-      pre_forward_core(kind, dir, n, M, xs + (size_t)r * ldx, (double *)(zA + (size_t)(r >> 1) * ldz) + (r & 1), P.trig,
-                       dsum + r, lane);
+      pre_forward_core(kind, dir, n, M, rowsB + r * ldz, (double *)(zA + (r >> 1) * ldz) + (r & 1), P.trig, dsum + r, lane);
     __syncthreads();
+    cur = zA;
+    oth = zB;
     run_passes<-1>(cur, oth, P, tid, nthr);
-    /* split: cur -> half-complex rows in oth (row pitch ldz doubles) */
+    /* split: cur -> half-complex rows in oth */
     double *hs = (double *)oth;
     const int nfq = M / 2 + 1;
-    for (int idx = tid; idx < T * nfq; idx += nthr) {
-      int t = idx / nfq, f = idx - t * nfq;
-      split_pair(cur + (size_t)t * ldz, hs + (size_t)(2 * t) * ldz, hs + (size_t)(2 * t + 1) * ldz, M, f);
-    }
+    for (int t = 0; t < T; ++t)
+      for (int f = tid; f < nfq; f += nthr) split_pair(cur + t * ldz, hs + (2 * t) * ldz, hs + (2 * t + 1) * ldz, M, f);
     __syncthreads();
-    for (int r = warp; r < rows; r += nwarp)
-      post_sequence(kind, dir, n, M, hs + (size_t)r * ldz, xs + (size_t)r * ldx, P.trig, dsum[r], lane);
+    /* post: half-complex rows (oth) -> result rows (cur, no longer needed) */
+    double *ys = (double *)cur;
+    for (int r = warp; r < rows; r += nwarp) post_sequence(kind, dir, n, M, hs + r * ldz, ys + r * ldz, P.trig, dsum[r], lane);
+    __syncthreads();
+    rowsA = ys;
   } else {
-    double *hs = (double *)zB;
-    for (int r = warp; r < rows; r += nwarp) pre_backward_core(kind, n, xs + (size_t)r * ldx, hs + (size_t)r * ldz, lane);
+    for (int r = warp; r < rows; r += nwarp) pre_backward_core(kind, n, rowsB + r * ldz, rowsA + r * ldz, lane);
     __syncthreads();
     const int nfq = M / 2 + 1;
-    for (int idx = tid; idx < T * nfq; idx += nthr) {
-      int t = idx / nfq, f = idx - t * nfq;
-      build_pair(zA + (size_t)t * ldz, hs + (size_t)(2 * t) * ldz, hs + (size_t)(2 * t + 1) * ldz, M, f);
-    }
+    for (int t = 0; t < T; ++t)
+      for (int f = tid; f < nfq; f += nthr) build_pair(zB + t * ldz, rowsA + (2 * t) * ldz, rowsA + (2 * t + 1) * ldz, M, f);
     __syncthreads();
+    cur = zB;
+    oth = zA;
     run_passes<1>(cur, oth, P, tid, nthr);
     /* extract: re/im of cur -> real rows in oth */
     double *us = (double *)oth;
-    for (int idx = tid; idx < T * M; idx += nthr) {
-      int t = idx / M, e = idx - t * M;
-      cpx v = cur[(size_t)t * ldz + e];
-      us[(size_t)(2 * t) * ldz + e] = v.x;
-      us[(size_t)(2 * t + 1) * ldz + e] = v.y;
-    }
+    for (int t = 0; t < T; ++t)
+      for (int e = tid; e < M; e += nthr) {
+        cpx v = cur[t * ldz + e];
+        us[(2 * t) * ldz + e] = v.x;
+        us[(2 * t + 1) * ldz + e] = v.y;
+      }
     __syncthreads();
-    for (int r = warp; r < rows; r += nwarp)
-      post_sequence(kind, dir, n, M, us + (size_t)r * ldz, xs + (size_t)r * ldx, P.trig, 0.0, lane);
+    double *ys = (double *)cur;
+    for (int r = warp; r < rows; r += nwarp) post_sequence(kind, dir, n, M, us + r * ldz, ys + r * ldz, P.trig, 0.0, lane);
+    __syncthreads();
+    rowsA = ys;
   }
-  __syncthreads();
   {
     double *out = (double *)P.out;
-    const int total = rows * n;
-    for (int idx = tid; idx < total; idx += nthr) {
-      int r, e;
-      tile_index(idx, rows, n, P.aout.lanes_t, r, e);
-      long long g = s0 + r;
-      if (g >= P.lot) continue;
-      int es = e;
-      double sg = 1.0;
-      if (kind == K_SINQ) {
-        if (dir < 0) sg = (e & 1) ? -1.0 : 1.0;
-        else es = n - 1 - e;
+    const long long inc_out = P.aout.inc;
+    CFB_TILE_LOOP(rows, n, P.aout.lanes_t, P.tx_out_log2, {
+      const long long o = off_out[r];
+      if (o >= 0) {
+        int es = e;
+        double sg = 1.0;
+        if (kind == K_SINQ) {
+          if (dir < 0) sg = (e & 1) ? -1.0 : 1.0;
+          else es = n - 1 - e;
+        }
+        out[o + e * inc_out] = sg * rowsA[r * ldz + es];
       }
-      out[batch_off(P.aout, g) + (long long)e * P.aout.inc] = sg * xs[(size_t)r * ldx + es];
-    }
+    })
   }
 }
 

@@ -13,11 +13,14 @@ enum Kind { K_C2C = 0, K_RFFT = 1, K_COST = 2, K_SINT = 3, K_COSQ = 4, K_SINQ = 
 #define CFB_ENGINE_THREADS 256
 
 struct PassDesc {
-  int radix;  // 2,3,4,5 or a generic odd prime
+  int radix;  // 2,3,4,5,8 or a generic odd prime
   int s;      // product of the radices of earlier passes
   int m;      // remaining length / radix
   int twoff;  // offset of this pass's twiddles in the plan table, laid out [k-1][p], p < m
   int rtoff;  // generic radix only: offset of the table exp(-2 pi i j / radix), j < radix
+  unsigned mag_s;   // ceil(2^32 / s):  b / s == __umulhi(b, mag_s) for b * s < 2^32 (s > 1)
+  unsigned mag_nb;  // ceil(2^32 / nb), nb = M / radix butterflies per sequence
+  unsigned mag_per; // generic radix: ceil(2^32 / (nb * (radix + 1) / 2))
 };
 
 /* element (g, e) of a batch lives at  (g / nlo) * jump_hi + (g % nlo) * jump_lo + e * inc  (units: elements) */
@@ -33,8 +36,9 @@ struct EngineParams {
   int M;          // length of the complex core transform (n, n-1 for cost, n+1 for sint)
   int nf;
   int T;    // complex sequences (c2c) or PAIRS of real sequences (other kinds) per CTA
-  int ldz;  // row pitch of the complex buffers (odd, >= M)
-  int ldx;  // row pitch of the real staging rows (odd, >= n + 1)
+  int ldz;  // row pitch of the complex buffers (odd, >= max(M, n)); real rows use the same pitch in doubles
+  int ldx;  // unused (kept for layout stability)
+  int tx_in_log2, tx_out_log2;  // loader / storer thread tiling: 2^tx threads walk the contiguous axis
   int aligned16;  // c2c: in and out are 16-byte aligned
   long long lot;  // sequences in the batch
   Addr ain, aout;

@@ -51,25 +51,24 @@ int engine_factor(int M, int *radix) {
     M /= 2;
     ++a;
   }
-  // power of two: as many 16s as possible, the remainder as 8/4/2 (no pass smaller than needed)
-  switch (a % 4) {
+  // power of two: as many 8s as possible, the remainder as 4s / one 2 (the engine keeps <= 8 points per thread)
+  switch (a % 3) {
     case 1:
-      if (a >= 5) {
-        radix[nf++] = 8;
+      if (a >= 4) {
         radix[nf++] = 4;
-        a -= 5;
+        radix[nf++] = 4;
+        a -= 4;
       } else {
         radix[nf++] = 2;
         a -= 1;
       }
       break;
     case 2: radix[nf++] = 4; a -= 2; break;
-    case 3: radix[nf++] = 8; a -= 3; break;
     default: break;
   }
-  while (a >= 4) {
-    radix[nf++] = 16;
-    a -= 4;
+  while (a >= 3) {
+    radix[nf++] = 8;
+    a -= 3;
   }
   while (M % 5 == 0) {
     radix[nf++] = 5;
@@ -141,6 +140,13 @@ const CorePlan *get_core_plan(int M) {
     pd.m = m;
     pd.twoff = (int)tw.size();
     pd.rtoff = 0;
+    {
+      auto magic = [](long long d) -> unsigned { return d <= 1 ? 0u : (unsigned)(((1ULL << 32) + d - 1) / d); };
+      const long long nb = M / r;
+      pd.mag_s = magic(s);
+      pd.mag_nb = magic(nb);
+      pd.mag_per = magic(nb * ((r + 1) / 2));
+    }
     if (m > 1)
       for (int kk = 1; kk < r; ++kk)
         for (int p = 0; p < m; ++p) {
@@ -148,7 +154,7 @@ const CorePlan *get_core_plan(int M) {
           unit_root((long long)p * kk, cur, &w.x, &w.y);
           tw.push_back(w);
         }
-    if (r > 5 && r != 8 && r != 16) {
+    if (r > 5 && r != 8) {
       pd.rtoff = (int)tw.size();
       for (int j = 0; j < r; ++j) {
         cpx w;

@@ -1,0 +1,62 @@
+"""Developer tool: device-resident timings of every BASELINE.json config shape (CUDA events, median of reps).
+Prints one line per case with algorithmic GB/s (one read + one write of the payload per pass)."""
+import ctypes, json, math, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import cfftpack_b200 as cb
+import fftlibs as fl
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        fn(); ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+    return ts[len(ts) // 2]
+
+def case(fam, n, lot, inc=None, jump=None, d="f"):
+    inc = 1 if inc is None else inc
+    jump = n if jump is None else jump
+    esz = 2 if fam == "cfft" else 1
+    span = (lot - 1) * jump + (n - 1) * inc + 1
+    x = (torch.rand(span * esz, device="cuda", dtype=torch.float64) - 0.5)
+    plan = cb.Plan(fam, n)
+    def run():
+        ier = plan.multi(d, x.data_ptr(), lot, jump, inc, span)
+        assert ier == 0, (ier, cb.last_error())
+    ms = timeit(run)
+    by = 2 * 8 * esz * n * lot
+    print(f"{fam}m{d} n={n:6d} lot={lot:6d} inc={inc:6d} jump={jump:6d}: {ms:8.3f} ms  {by / ms / 1e6:8.1f} GB/s  ({by / ms / 1e6 / 65.475:5.1f}% of measured HBM)", flush=True)
+
+def case2d(l, m, d="f"):
+    c = torch.rand(l * m * 2, device="cuda", dtype=torch.float64) - 0.5
+    P = fl.Lib(fl.product())
+    ws, ls, ier = P.init2(l, m)
+    I = ctypes.c_int; ierc = I(-1); dummy = ctypes.c_double(0)
+    args = (ctypes.byref(I(l)), ctypes.byref(I(l)), ctypes.byref(I(m)), ctypes.c_void_p(c.data_ptr()), fl.P(ws),
+            ctypes.byref(I(ls)), ctypes.byref(dummy), ctypes.byref(I(2 * l * m)), ctypes.byref(ierc))
+    fn = getattr(fl.product(), "cfft2" + d + "_")
+    def run():
+        fn(*args); assert ierc.value == 0, cb.last_error()
+    ms = timeit(run, reps=5, warm=2)
+    by = 2 * 2 * 16 * l * m  # two passes minimum
+    print(f"cfft2{d} {l}x{m}: {ms:8.3f} ms  {by / ms / 1e6:8.1f} GB/s vs 2-pass minimum ({by / ms / 1e6 / 65.475:5.1f}% of measured HBM)", flush=True)
+
+which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c2", "c3", "c4", "c5", "misc"]
+if "c2" in which:
+    case("cfft", 4096, 65536); case("cfft", 4096, 65536, d="b")
+if "c3" in which:
+    case("rfft", 4096, 65536); case("rfft", 4096, 65536, d="b")
+if "c4" in which:
+    for fam, n in (("cost", 1001), ("sint", 1000), ("cosq", 1000), ("cosq", 1001), ("cost", 1000), ("sint", 1001)):
+        case(fam, n, 32768); case(fam, n, 32768, d="b")
+if "c5" in which:
+    case2d(16384, 16384); case2d(4096, 4096)
+if "misc" in which:
+    case("cfft", 1024, 262144); case("cfft", 256, 1048576); case("cfft", 64, 4194304); case("cfft", 8192, 32768)
+    case("cfft", 1000, 262144); case("cfft", 4096, 65536, inc=65536, jump=1); case("rfft", 1000, 262144)
+    case("cfft", 16384, 16384); case("cfft", 16384, 16384, inc=16384, jump=1)

@@ -67,6 +67,7 @@ void run(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
 #define gridDim (cfbsim::cur->gdim)
 #define __syncthreads() cfbsim::yield_barrier()
 #define __syncwarp(...) cfbsim::warp_barrier()
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 template <class T>
