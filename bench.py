@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "10"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -66,7 +66,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """start of the timed region: earlier samples (warm-up, idle) are dropped"""
+        self.t0 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -78,7 +82,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        for ts, ln in self.lines:
+            if ts < t0:
+                continue
             f = [v.strip() for v in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -235,11 +242,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)  # let nvidia-smi come up before the timed region
     # in-place forward transforms scale by 1/N each step, so values shrink towards 0 without ever leaving FP64
     # normal range for K <= 20 (4096^-20 ~ 1e-72); timing is data independent.
     launches0 = cb.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    sampler.mark()
     ev[0].record(stream)
     for i in range(args.steps):
         step()

@@ -9,6 +9,7 @@
  */
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -145,6 +146,73 @@ static bool view_close(DeviceView &v, bool ok) {
   return ok && s;
 }
 
+/* ---- batched host arrays: pipeline lot-chunks through HBM so that the H2D copy of chunk c+1, the transform of
+ * chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex; the copy engines are independent).
+ * Applies when the sequences are not interleaved (jump >= extent of one sequence). ---- */
+static const int PIPE_BUFS = 3;
+struct PipeStreams {
+  cudaStream_t st[PIPE_BUFS] = {0, 0, 0};
+  bool ok = false;
+  ~PipeStreams() {
+    if (ok)
+      for (auto s : st) cudaStreamDestroy(s);
+  }
+};
+static thread_local PipeStreams t_pipe;
+
+template <class F>
+static bool run_on_array(void *user, size_t esz, long long lot, long long jump, int n, long long inc, F &&fn) {
+  const long long seq_span = inc * (long long)(n - 1) + 1;
+  const size_t total = (size_t)((lot - 1) * jump + seq_span) * esz;
+  if (!device_ready()) return false;
+  cudaPointerAttributes at;
+  memset(&at, 0, sizeof(at));
+  if (cudaPointerGetAttributes(&at, user) != cudaSuccess) {
+    cudaGetLastError();
+    at.type = cudaMemoryTypeUnregistered;
+  }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return fn(user, lot);
+  static const size_t CHUNK = [] {  // bytes per pipeline stage; CFB200_PIPE_CHUNK_KB overrides (tests)
+    const char *e = getenv("CFB200_PIPE_CHUNK_KB");
+    return e ? (size_t)atoll(e) << 10 : (size_t)64 << 20;
+  }();
+  const bool pipelined = lot >= 4 && jump >= seq_span && total >= 2 * CHUNK && at.type == cudaMemoryTypeHost;
+  if (!pipelined) {
+    DeviceView v;
+    bool ok = view_open(user, total, v);
+    if (ok) ok = fn(v.dev, lot);
+    return view_close(v, ok);
+  }
+  if (!t_pipe.ok) {
+    for (auto &s : t_pipe.st)
+      if (!cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+    t_pipe.ok = true;
+  }
+  long long per = (long long)(CHUNK / ((size_t)jump * esz));
+  if (per < 1) per = 1;
+  const size_t buf_bytes = (size_t)((per - 1) * jump + seq_span) * esz;
+  void *bufs[PIPE_BUFS];
+  for (int i = 0; i < PIPE_BUFS; ++i)
+    if (!(bufs[i] = scratch_get(1 + i, buf_bytes))) return false;
+  cudaStream_t saved = t_stream;
+  if (!cuda_ok(cudaStreamSynchronize(saved), "cudaStreamSynchronize")) return false;
+  bool ok = true;
+  int c = 0;
+  for (long long m0 = 0; m0 < lot && ok; m0 += per, ++c) {
+    const long long lc = (lot - m0) < per ? (lot - m0) : per;
+    const size_t bytes = (size_t)((lc - 1) * jump + seq_span) * esz;
+    char *h = (char *)user + (size_t)m0 * jump * esz;
+    const int b = c % PIPE_BUFS;
+    t_stream = t_pipe.st[b];
+    ok = cuda_ok(cudaMemcpyAsync(bufs[b], h, bytes, cudaMemcpyHostToDevice, t_stream), "cudaMemcpyAsync(H2D)") &&
+         fn(bufs[b], lc) &&
+         cuda_ok(cudaMemcpyAsync(h, bufs[b], bytes, cudaMemcpyDeviceToHost, t_stream), "cudaMemcpyAsync(D2H)");
+  }
+  for (auto s : t_pipe.st) ok = cuda_ok(cudaStreamSynchronize(s), "cudaStreamSynchronize") && ok;
+  t_stream = saved;
+  return ok;
+}
+
 static inline long long span1(int n, int inc) { return (long long)inc * (n - 1) + 1; }
 static inline long long spanm(int lot, int jump, int n, int inc) {
   return (long long)(lot - 1) * jump + (long long)inc * (n - 1) + 1;
@@ -184,10 +252,8 @@ static int complex_multi(int *lot, int *jump, int *n, int *inc, void *c, int *le
   else if ((long long)*lenwrk < 2LL * *lot * *n) *ier = 3;
   else if (!strides_consistent(*inc, *jump, *n, *lot)) *ier = 4;
   if (*ier || *n == 1) return 0;
-  DeviceView v;
-  bool ok = view_open(c, (size_t)spanm(*lot, *jump, *n, *inc) * 16, v);
-  if (ok) ok = run_c2c(*n, *lot, *inc, *jump, dir, v.dev);
-  ok = view_close(v, ok);
+  const int nn = *n, ii = *inc, jj = *jump;
+  bool ok = run_on_array(c, 16, *lot, jj, nn, ii, [&](void *dev, long long l) { return run_c2c(nn, l, ii, jj, dir, dev); });
   if (!ok) *ier = -1;
   return 0;
 }
@@ -262,10 +328,9 @@ static int real_multi(int kind, int *lot, int *jump, int *n, int *inc, double *x
   else if ((long long)*lenwrk < fam_lenwrk(kind, *n, *lot, true)) *ier = 3;
   else if (!strides_consistent(*inc, *jump, *n, *lot)) *ier = 4;
   if (*ier || *n == 1) return 0;
-  DeviceView v;
-  bool ok = view_open(x, (size_t)spanm(*lot, *jump, *n, *inc) * 8, v);
-  if (ok) ok = run_real(kind, *n, *lot, *inc, *jump, dir, (double *)v.dev);
-  ok = view_close(v, ok);
+  const int nn = *n, ii = *inc, jj = *jump;
+  bool ok = run_on_array(x, 8, *lot, jj, nn, ii,
+                         [&](void *dev, long long l) { return run_real(kind, nn, l, ii, jj, dir, (double *)dev); });
   if (!ok) *ier = -1;
   return 0;
 }

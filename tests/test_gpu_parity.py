@@ -266,3 +266,17 @@ def test_cfft2_16384_device_roundtrip_and_separability():
     back = (v[:, None] * u[None, :])
     err = float((torch.view_as_real(c) - torch.view_as_real(back)).norm() / torch.view_as_real(back).norm())
     assert err <= fl.tol(l * m), err
+
+
+def test_pinned_host_arrays_take_the_pipelined_path():
+    """a pinned host batch >= 128 MiB is staged in lot-chunks on three streams; result must equal the device path"""
+    torch = _torch()
+    import cfftpack_b200 as cb
+    for fam, n, lot, esz in (("cfft", 4096, 2500, 2), ("rfft", 4096, 4500, 1)):
+        h = torch.empty(lot * n * esz, dtype=torch.float64, pin_memory=True).uniform_(-1, 1)
+        d = h.cuda()
+        plan = cb.Plan(fam, n)
+        assert plan.multi("f", d.data_ptr(), lot, n, 1, lot * n) == 0
+        cb.synchronize()
+        assert plan.multi("f", h.data_ptr(), lot, n, 1, lot * n) == 0, cb.last_error()
+        assert torch.equal(h, d.cpu()), fam

@@ -101,3 +101,33 @@ def test_cfft2(libs):
                 for j in range(m):
                     pad[j * ldim: j * ldim + l] = False
                 assert np.array_equal(a[pad], c[pad])
+
+
+def test_pipelined_host_staging(libs):
+    """pinned host arrays go through HBM in lot-chunks on three streams; chunk size forced small here"""
+    import ctypes
+    import subprocess
+    import sys
+    code = """
+import sys, ctypes, numpy as np
+sys.path.insert(0, %r)
+import fftlibs as fl
+S, O = fl.Lib(fl.sim()), fl.Lib(fl.oracle(), 'orc_')
+for fam, n, lot, jump in (('cfft', 64, 37, 64), ('rfft', 100, 29, 103), ('cost', 33, 50, 40), ('cfft', 128, 9, 128)):
+    x = fl.rand_input(fam, (lot - 1) * jump + n, 5)
+    fl.sim().cfb200_sim_mark_pinned(fl.P(x), ctypes.c_size_t(0))
+    want, ib = O.runm(fam, 'f', lot, jump, n, 1, x, lenx=len(x))
+    y = np.array(x, copy=True)
+    fl.sim().cfb200_sim_mark_pinned(fl.P(y), ctypes.c_size_t(y.nbytes))
+    ws, _ = S.init(fam, n, multi=True)
+    ier = ctypes.c_int(-1); I = ctypes.c_int
+    wk = np.zeros(8)
+    getattr(fl.sim(), fam + 'mf_')(ctypes.byref(I(lot)), ctypes.byref(I(jump)), ctypes.byref(I(n)), ctypes.byref(I(1)), fl.P(y),
+        ctypes.byref(I(len(y))), fl.P(ws), ctypes.byref(I(fl.lensav(fam, n))), fl.P(wk), ctypes.byref(I(fl.lenwrk(fam, n, lot))), ctypes.byref(ier))
+    assert ier.value == 0 == ib, (fam, ier.value)
+    assert fl.rel_l2(y, want) <= fl.tol(n), (fam, n, fl.rel_l2(y, want))
+print('ok')
+""" % os.path.join(fl.ROOT, "tests")
+    env = dict(os.environ, CFB200_PIPE_CHUNK_KB="4")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

@@ -128,6 +128,7 @@ void run(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) 
 }  // namespace cfbsim
 
 static std::map<uintptr_t, size_t> g_dev;
+static std::map<uintptr_t, size_t> g_pinned;
 static std::mutex g_dev_mu;
 void cfbsim_mark_device(const void *p, size_t bytes) {
   std::lock_guard<std::mutex> lk(g_dev_mu);
@@ -141,4 +142,16 @@ int cfbsim_is_device(const void *p) {
   --it;
   return (uintptr_t)p < it->first + it->second;
 }
+int cfbsim_is_pinned(const void *p) {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  auto it = g_pinned.upper_bound((uintptr_t)p);
+  if (it == g_pinned.begin()) return 0;
+  --it;
+  return (uintptr_t)p < it->first + it->second;
+}
 extern "C" void cfb200_sim_mark_device(const void *p, size_t bytes) { cfbsim_mark_device(p, bytes); }
+extern "C" void cfb200_sim_mark_pinned(const void *p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (bytes == 0) g_pinned.erase((uintptr_t)p);
+  else g_pinned[(uintptr_t)p] = bytes;
+}

@@ -159,8 +159,9 @@ static inline cudaError_t cudaGetDeviceCount(int *n) {
 /* every pointer looks like pageable host memory unless registered with cfbsim_mark_device() */
 void cfbsim_mark_device(const void *p, size_t bytes);
 int cfbsim_is_device(const void *p);
+int cfbsim_is_pinned(const void *p);
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p) {
-  a->type = cfbsim_is_device(p) ? cudaMemoryTypeDevice : cudaMemoryTypeUnregistered;
+  a->type = cfbsim_is_device(p) ? cudaMemoryTypeDevice : cfbsim_is_pinned(p) ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered;
   a->device = 0;
   return 0;
 }
