@@ -181,13 +181,51 @@ def run_reference(args, fam, n, lot, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def run_cfft2(args, torch, dist, cb, rank, local_rank, world, barrier):
+    """BASELINE configs[4]: cfft2f 2-D c2c FP64 l x l, column slabs over the ranks, all-to-all transposes (strong scaling)."""
+    from cfftpack_b200.dist import Cfft2Sharded
+    l = m = args.l2d
+    plan = Cfft2Sharded(l, m)
+    g = torch.Generator(device="cuda").manual_seed(99 + rank)
+    slab = torch.view_as_complex(torch.rand(m // world, l, 2, generator=g, device="cuda", dtype=torch.float64) - 0.5)
+    for _ in range(max(args.warmup, 2)):
+        plan.forward(slab)
+    barrier()
+    steps = min(args.steps, 10)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = cb.launch_count()
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        plan.forward(slab)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    hbm_bytes = 2 * 2 * 16 * l * m  # two read+write passes minimum (SURVEY 8(d))
+    link_bytes = 2 * 16 * l * m * (world - 1) // (world * world)  # per GPU, both exchanges
+    if rank == 0:
+        print(json.dumps({
+            "metric": f"cfft2f FP64 {l}x{m} algorithmic HBM GB/s (2-pass minimum)", "value": hbm_bytes / (ms * 1e-3) / 1e9,
+            "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 2), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "gflops_5nlogn": 5.0 * l * m * math.log2(l * m) / (ms * 1e-3) / 1e9,
+            "config": {"workload": f"cfft2f {l}x{m} c128 column slabs, all-to-all transpose x2 (BASELINE configs[4])"},
+            "nvlink_bytes_per_gpu_per_step": link_bytes,
+            "nvlink_floor_ms_at_770GBps": link_bytes / 770e9 * 1e3,
+            "gpu_launches": int(cb.launch_count() - launches0)}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="cfftm", choices=["cfftm", "rfftm"])
+    ap.add_argument("--workload", default="cfftm", choices=["cfftm", "rfftm", "cfft2"])
+    ap.add_argument("--l2d", type=int, default=16384, help="cfft2 workload: matrix is l2d x l2d (BASELINE configs[4])")
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--lot", type=int, default=LOT_DEFAULT)
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -224,6 +262,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.workload == "cfft2":
+        run_cfft2(args, torch, dist, cb, rank, local_rank, world, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     esz = 2 if fam == "cfft" else 1
     stream = torch.cuda.current_stream()
     cb.set_stream(stream.cuda_stream)

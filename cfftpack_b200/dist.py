@@ -1,0 +1,92 @@
+"""Multi-GPU host logic (one process per GPU, torch.distributed for the plumbing).
+
+ * Batched transforms (`cfftm*`, `rfftm*`, `costm*`, ...) shard by lot with NO data-path collective: `shard_lot`.
+ * `Cfft2Sharded`: the reference's 2-D transform `cfft2f_/cfft2b_` (cfftpack/fftpack.c:2363, :2285 -- two `cfftmf_`
+   sweeps, :2408-2426) on a matrix distributed as column slabs, with ONE exchange per dimension switch
+   (SURVEY 8(e)): local length-l transforms down the columns, all-to-all transpose (NCCL over NVLink on GPUs),
+   local length-m transforms along the rows, all-to-all back to the caller's slab layout.
+
+The local transforms are calls into the C ABI (`cfftmf_`/`cfftmb_`); nothing here computes a transform.
+"""
+import ctypes
+
+_I = ctypes.c_int
+
+
+def shard_lot(lot, rank, world):
+    """contiguous lot range [m0, m1) owned by `rank`; with jump = N this is a contiguous byte range"""
+    return lot * rank // world, lot * (rank + 1) // world
+
+
+class Cfft2Sharded:
+    """c(l, m) column-major, rank g owns columns [g*m/G, (g+1)*m/G) as a contiguous slab `c_loc[m/G][l]`."""
+
+    def __init__(self, l, m, group=None, lib=None):
+        import numpy as np
+        import torch.distributed as dist
+        if lib is None:
+            from . import lib as product_lib
+            lib = product_lib
+        self.lib, self.group = lib, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        G = self.world
+        if l % G or m % G:
+            raise ValueError(f"l={l} and m={m} must be multiples of the number of ranks {G}")
+        self.l, self.m, self.l_loc, self.m_loc = l, m, l // G, m // G
+        from . import lensav
+        self.ws = {}
+        for n in {l, m}:
+            ls = lensav("cfft", n)
+            ws = np.zeros(ls + 8)
+            ier = _I(-1)
+            lib.cfftmi_(ctypes.byref(_I(n)), ws.ctypes.data_as(ctypes.c_void_p), ctypes.byref(_I(ls)), ctypes.byref(ier))
+            if ier.value:
+                raise RuntimeError(f"cfftmi_ n={n}: ier={ier.value}")
+            self.ws[n] = (ws, ls)
+        self._send = self._recv = None
+
+    def _cfftm(self, direction, ptr, lot, jump, n, inc, lenc):
+        ws, ls = self.ws[n]
+        ier, dummy = _I(-1), ctypes.c_double(0.0)
+        getattr(self.lib, "cfftm" + direction + "_")(
+            ctypes.byref(_I(lot)), ctypes.byref(_I(jump)), ctypes.byref(_I(n)), ctypes.byref(_I(inc)),
+            ctypes.c_void_p(ptr), ctypes.byref(_I(lenc)), ws.ctypes.data_as(ctypes.c_void_p), ctypes.byref(_I(ls)),
+            ctypes.byref(dummy), ctypes.byref(_I(min(2 * lot * n, 2**31 - 1))), ctypes.byref(ier))
+        if ier.value:
+            raise RuntimeError(f"cfftm{direction}_ lot={lot} n={n} inc={inc} jump={jump}: ier={ier.value}")
+
+    def transform(self, c_loc, direction):
+        """in place on the complex128 slab c_loc of shape [m_loc, l] (contiguous); direction 'f' or 'b'"""
+        import torch
+        import torch.distributed as dist
+        G, l, m, l_loc, m_loc = self.world, self.l, self.m, self.l_loc, self.m_loc
+        assert c_loc.dtype == torch.complex128 and c_loc.is_contiguous() and tuple(c_loc.shape) == (m_loc, l)
+        if c_loc.is_cuda:  # stream order: library kernels, torch copies and the collectives all follow torch's stream
+            self.lib.cfb200_set_stream(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        # 1. columns: lot = m_loc sequences of length l, contiguous
+        self._cfftm(direction, c_loc.data_ptr(), m_loc, l, l, 1, m_loc * l)
+        if G == 1:
+            # rows on the same slab: lot = l, jump = 1, n = m, inc = l (the reference's first sweep, fftpack.c:2408)
+            self._cfftm(direction, c_loc.data_ptr(), l, 1, m, l, m * l)
+            return c_loc
+        if self._send is None or self._send.device != c_loc.device:
+            self._send = torch.empty(G, m_loc, l_loc, dtype=torch.complex128, device=c_loc.device)
+            self._recv = torch.empty(G, m_loc, l_loc, dtype=torch.complex128, device=c_loc.device)
+        send, recv = self._send, self._recv
+        # 2. transpose exchange: block (row slab r, my columns) -> rank r
+        send.copy_(c_loc.view(m_loc, G, l_loc).permute(1, 0, 2))
+        dist.all_to_all_single(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1), group=self.group)
+        # recv is d(l_loc, m) column-major: element (i_loc, j) at j*l_loc + i_loc
+        # 3. rows: lot = l_loc, jump = 1, n = m, inc = l_loc
+        self._cfftm(direction, recv.data_ptr(), l_loc, 1, m, l_loc, m * l_loc)
+        # 4. back to column slabs
+        dist.all_to_all_single(torch.view_as_real(send).view(-1), torch.view_as_real(recv).view(-1), group=self.group)
+        c_loc.view(m_loc, G, l_loc).copy_(send.permute(1, 0, 2))
+        return c_loc
+
+    def forward(self, c_loc):
+        return self.transform(c_loc, "f")
+
+    def backward(self, c_loc):
+        return self.transform(c_loc, "b")

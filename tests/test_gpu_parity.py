@@ -280,3 +280,25 @@ def test_pinned_host_arrays_take_the_pipelined_path():
         cb.synchronize()
         assert plan.multi("f", h.data_ptr(), lot, n, 1, lot * n) == 0, cb.last_error()
         assert torch.equal(h, d.cpu()), fam
+
+
+def test_reference_own_test_programs_relinked_against_the_cuda_library():
+    """the reference's wrapper layer (cfftpack.c, cfftextra.c) and its own asserting test
+    (test/testall.c: DCT/DST families vs test/naivepack.c, abs tol 1e-13, N = 2, 32, 60) linked against
+    libcfftpack_b200.so instead of fftpack.c.  Built by oracle/Makefile where /root/reference exists."""
+    import os
+    import subprocess
+    exe = os.path.join(fl.ROOT, "oracle", "_ref", "testall_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/testall_b200 not prebuilt")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.stdout.count("DCT tests passed") == 3 and out.stdout.count("DST tests passed") == 2, out.stdout + out.stderr
+    assert "Assertion failed" not in out.stdout + out.stderr
+    # test/ftest.c (print-only in the reference): cosqmb_/cosqmf_ on a 10x10 grid in both (lot, jump, inc) orientations
+    a = subprocess.run([os.path.join(fl.ROOT, "oracle", "_ref", "ftest_b200")], capture_output=True, text=True, timeout=120).stdout
+    b = subprocess.run([os.path.join(fl.ROOT, "oracle", "_ref", "ftest_ref")], capture_output=True, text=True, timeout=120).stdout
+    import re
+    fa = [float(v) for v in re.findall(r"-?\d+\.\d+", a)]
+    fb = [float(v) for v in re.findall(r"-?\d+\.\d+", b)]
+    assert len(fa) == len(fb) > 100
+    assert max(abs(u - v) for u, v in zip(fa, fb)) <= 0.0100001  # printed with two decimals
