@@ -21,7 +21,7 @@ namespace cfb {
 static const size_t SMEM_MAX = 227 * 1024;      // opt-in limit per CTA on sm_100
 static const size_t SMEM_TARGET = 72 * 1024;    // aim: three CTAs per SM for the streaming kernels
 
-int engine_max_c2c() { return (int)((SMEM_MAX - 1024) / 32) - 2; }
+int engine_max_c2c() { return (int)((SMEM_MAX - 1024) / 48 * 8 / 9) - 2; }
 int engine_max_real() { return (int)((SMEM_MAX - 1024) / 32) - 4; }
 
 static bool engine_attr_once() {
@@ -29,16 +29,25 @@ static bool engine_attr_once() {
   static bool ok = true;
   std::call_once(once, [] {
     ok = cuda_ok(cudaFuncSetAttribute(engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
-                 "cudaFuncSetAttribute(engine_kernel)");
+                 "cudaFuncSetAttribute(engine_kernel)") &&
+         cuda_ok(cudaFuncSetAttribute(engine_c2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
+                 "cudaFuncSetAttribute(engine_c2c_kernel)") &&
+         cuda_ok(cudaFuncSetAttribute(engine_c2c_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
+                 "cudaFuncSetAttribute(engine_c2c_kernel, carveout)") &&
+         cuda_ok(cudaFuncSetAttribute(engine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
+                 "cudaFuncSetAttribute(engine_kernel, carveout)");
   });
   return ok;
 }
+
+static const size_t TW_SMEM_MAX = 16 * 1024;  // plan twiddle tables up to this size are copied to shared memory
 
 static void fill_passes(EngineParams &P, const CorePlan *cp) {
   P.M = cp->M;
   P.nf = cp->nf;
   for (int i = 0; i < cp->nf; ++i) P.pass[i] = cp->pass[i];
   P.tw = cp->d_tw;
+  P.tw_smem = (cp->tw_count > 0 && cp->tw_count * sizeof(cpx) <= TW_SMEM_MAX) ? (int)cp->tw_count : 0;
 }
 
 static Addr make_addr(long long inc, long long jump_lo, long long jump_hi, long long nlo) {
@@ -52,6 +61,16 @@ static Addr make_addr(long long inc, long long jump_lo, long long jump_hi, long 
   return a;
 }
 
+/* split n = n1 * n2 with both factors as close to sqrt(n) as the limit allows; 0 if impossible */
+static int four_step_split(int n, int limit) {
+  int best = 0;
+  for (int d = 1; (long long)d * d <= n; ++d)
+    if (n % d == 0 && n / d <= limit) {
+      best = d;  // largest d <= sqrt(n); n/d shrinks as d grows
+    }
+  return best;  // n1 = best (<= n2 = n / best)
+}
+
 static int log2_ceil_capped(long long v, int cap) {
   int l = 0;
   while ((1LL << l) < v && l < cap) ++l;
@@ -63,46 +82,56 @@ static bool launch_engine(EngineParams &P) {
   if (!engine_attr_once()) return false;
   const bool real = P.kind != K_C2C;
   const int len = real ? P.n : P.M;  // elements per row that cross the global-memory boundary
-  P.ldz = (P.M > P.n ? P.M : P.n) | 1;
+  // complex rows: one pad slot per 2^padshift elements when the first radix is a power of two
+  P.padshift = 31;
+  if (!real && P.nf > 0) {
+    const int r1 = P.pass[0].radix;
+    if (r1 == 2) P.padshift = 1;
+    if (r1 == 4) P.padshift = 2;
+    if (r1 == 8) P.padshift = 3;
+  }
+  const int longest = P.M > P.n ? P.M : P.n;
+  P.ldz = (longest + ((longest - 1) >> P.padshift) + 1) | 1;
   P.ldx = 0;
-  const size_t per = (size_t)P.ldz * 32 + (real ? 64 : 32);  // per sequence (c2c) or per pair (real kinds)
+  // bytes per sequence (c2c: three complex rows -- two landing buffers + the ping-pong partner -- and double-buffered
+  // row tables) or per pair (real kinds: two complex rows and the row tables)
+  const size_t per = real ? (size_t)P.ldz * 32 + 64 : (size_t)P.ldz * 48 + 64;
+  const size_t fixed = 64 + (size_t)P.tw_smem * sizeof(cpx);
   const long long units = real ? (P.lot + 1) / 2 : P.lot;
-  if (per + 64 > SMEM_MAX) {
-    set_error("length %d does not fit one CTA (%zu bytes)", P.n, per);
+  if (per + fixed > SMEM_MAX) {
+    set_error("length %d does not fit one CTA (%zu bytes)", P.n, per + fixed);
     return false;
   }
-  long long T = (long long)(SMEM_TARGET / per);
+  long long T = (long long)((SMEM_TARGET - (fixed < SMEM_TARGET / 2 ? fixed : 0)) / per);
   const bool strided = P.ain.lanes_t || P.aout.lanes_t;
   // batch-contiguous layouts want at least 8 sequences side by side (128-byte runs of 16-byte elements)
   const long long want = strided ? (real ? 4 : 8) : 1;
-  if (T < want) T = (long long)((SMEM_MAX - 64) / per) < want ? (long long)((SMEM_MAX - 64) / per) : want;
+  const long long tmax = (long long)((SMEM_MAX - fixed) / per);
+  if (T < want) T = tmax < want ? tmax : want;
   if (T < 1) T = 1;
   if (T > 32) T = 32;
+  if (strided && T >= 8) {  // whole 128-byte runs along the batch axis: a power of two of rows
+    long long p2 = 8;
+    while (p2 * 2 <= T) p2 *= 2;
+    T = p2;
+  }
   if (T > units) T = units;
   P.T = (int)T;
   const long long rows = real ? 2 * T : T;
   // thread tiling of the loader/storer: threads along the contiguous axis first
   P.tx_in_log2 = log2_ceil_capped(P.ain.lanes_t ? rows : len, 8);
   P.tx_out_log2 = log2_ceil_capped(P.aout.lanes_t ? rows : len, 8);
-  const size_t smem = per * (size_t)T + 64;
-  const long long grid = (units + T - 1) / T;
-  if (grid > 2147483647LL) {
-    set_error("batch too large");
-    return false;
-  }
-  CFB_LAUNCH(engine_kernel, (unsigned)grid, CFB_ENGINE_THREADS, smem, current_stream(), P);
+  const size_t smem = per * (size_t)T + fixed;
+  P.ntiles = (units + T - 1) / T;
+  long long per_sm = (long long)((SMEM_MAX + 1024) / (smem + 1024));
+  if (per_sm > 3) per_sm = 3;  // register-limited (launch bounds)
+  if (per_sm < 1) per_sm = 1;
+  long long grid = per_sm * sm_count();
+  if (grid > P.ntiles) grid = P.ntiles;
+  if (real) CFB_LAUNCH(engine_kernel, (unsigned)grid, CFB_ENGINE_THREADS, smem, current_stream(), P);
+  else CFB_LAUNCH(engine_c2c_kernel, (unsigned)grid, CFB_ENGINE_THREADS, smem, current_stream(), P);
   count_launch();
-  return cuda_ok(cudaGetLastError(), "engine_kernel launch");
-}
-
-/* split n = n1 * n2 with both factors as close to sqrt(n) as the limit allows; 0 if impossible */
-static int four_step_split(int n, int limit) {
-  int best = 0;
-  for (int d = 1; (long long)d * d <= n; ++d)
-    if (n % d == 0 && n / d <= limit) {
-      best = d;  // largest d <= sqrt(n); n/d shrinks as d grows
-    }
-  return best;  // n1 = best (<= n2 = n / best)
+  return cuda_ok(cudaGetLastError(), "engine kernel launch");
 }
 
 bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void *c) {
@@ -115,7 +144,13 @@ bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void 
   P.dir = dir;
   P.n = n;
   P.aligned16 = aligned;
-  if (n <= engine_max_c2c()) {
+  // batch-contiguous layouts need >= 8 rows side by side in one CTA for full 128-byte runs; when a sequence is too
+  // long for that, the four-step split (short sub-transforms, many rows per CTA) is the faster route
+  const long long ainc0 = inc < 0 ? -inc : inc, ajump0 = jump < 0 ? -jump : jump;
+  const bool want_rows = ajump0 < ainc0 && lot >= 8;
+  const bool split_for_rows = want_rows && (SMEM_MAX - 64) / ((size_t)(n | 1) * 32 + 32) < 8 && n >= 256 &&
+                              four_step_split(n, engine_max_c2c()) > 1;
+  if (n <= engine_max_c2c() && !split_for_rows) {
     const CorePlan *cp = get_core_plan(n);
     if (!cp) return false;
     fill_passes(P, cp);
@@ -142,24 +177,39 @@ bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void 
   if (!p1 || !p2 || !rp) return false;
   cpx *scr = (cpx *)scratch_get(0, (size_t)lot * n * sizeof(cpx));
   if (!scr) return false;
-  // step 1
+  const long long ainc = inc < 0 ? -inc : inc, ajump = jump < 0 ? -jump : jump;
+  const bool batch_fast = ajump < ainc && lot > 1;  // interleaved layouts: the batch index is the contiguous axis
+  P.fs_tw = rp->d_w;
+  P.fs_n = n;
+  P.fs_shift = rp->shift;
+  // step 1: rows (m, j2), transform over j1, twiddle W_n^(j2*k1) on store
   fill_passes(P, p1);
   P.n = n1;
   P.lot = lot * n2;
-  P.ain = make_addr((long long)n2 * inc, inc, jump, n2);
-  P.aout = make_addr(n2, 1, n, n2);
+  if (!batch_fast) {  // row g = m*n2 + j2 (j2 fast); scratch S[m][k1][j2]
+    P.ain = make_addr((long long)n2 * inc, inc, jump, n2);
+    P.aout = make_addr(n2, 1, n, n2);
+    P.fs_from_hi = 0;
+  } else {  // row g = j2*lot + m (m fast); scratch S[k1][j2][m]
+    P.ain = make_addr((long long)n2 * inc, jump, inc, lot);
+    P.aout = make_addr((long long)n2 * lot, 1, lot, lot);
+    P.fs_from_hi = 1;
+  }
   P.in = c;
   P.out = scr;
   P.scale = 1.0;
-  P.fs_tw = rp->d_w;
-  P.fs_n = n;
   if (!launch_engine(P)) return false;
-  // step 2
+  // step 2: rows (m, k1), transform over j2, output element k2 goes to index k1 + n1*k2
   fill_passes(P, p2);
   P.n = n2;
   P.lot = lot * n1;
-  P.ain = make_addr(1, n2, n, n1);
-  P.aout = make_addr((long long)n1 * inc, inc, jump, n1);
+  if (!batch_fast) {  // row g = m*n1 + k1
+    P.ain = make_addr(1, n2, n, n1);
+    P.aout = make_addr((long long)n1 * inc, inc, jump, n1);
+  } else {  // row g = k1*lot + m
+    P.ain = make_addr(lot, 1, (long long)n2 * lot, lot);
+    P.aout = make_addr((long long)n1 * inc, jump, inc, lot);
+  }
   P.in = scr;
   P.out = c;
   P.scale = dir < 0 ? 1.0 / (double)n : 1.0;

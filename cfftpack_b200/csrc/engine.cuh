@@ -23,16 +23,20 @@
 #define CFB_ENGINE_CUH
 #include "butterfly.cuh"
 #include "engine_types.h"
+#include "tma.cuh"
 
 namespace cfb {
 
 /* ------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ int fast_div(int n, int d, unsigned mag) { return d == 1 ? n : (int)__umulhi((unsigned)n, mag); }
+/* padded position of element e inside a shared-memory row: one extra slot every 2^ps elements (ps = 31: none).
+ * With ps = log2 of the first radix the scattered stores of the first pass are bank-conflict free. */
+__device__ __forceinline__ int padx(int e, int ps) { return e + (e >> ps); }
 
 /* one radix-R pass over T sequences: src, dst are [T][ldz] complex arrays in shared memory       */
 template <int R, int DIR>
 __device__ __forceinline__ void pass_fixed(const cpx *__restrict__ src, cpx *__restrict__ dst, int T, int ldz, int M,
-                                           const PassDesc &pd, const cpx *__restrict__ tw, int tid, int nthr) {
+                                           const PassDesc &pd, const cpx *__restrict__ tw, int tid, int nthr, int ps) {
   const int nb = M / R;  // butterflies per sequence
   const int total = nb * T;
   const int s = pd.s, m = pd.m;
@@ -41,18 +45,19 @@ __device__ __forceinline__ void pass_fixed(const cpx *__restrict__ src, cpx *__r
     int t = fast_div(idx, nb, pd.mag_nb), b = idx - t * nb;
     int p = fast_div(b, s, pd.mag_s), q = b - p * s;
     cpx a[R];
-    const cpx *sp = src + t * ldz + b;
+    const cpx *sp = src + t * ldz;
 #pragma unroll
-    for (int j = 0; j < R; ++j) a[j] = sp[j * nb];
+    for (int j = 0; j < R; ++j) a[j] = sp[padx(b + j * nb, ps)];
     Dft<R, DIR>::run(a);
-    cpx *dp = dst + t * ldz + q + s * R * p;
-    dp[0] = a[0];
+    cpx *dp = dst + t * ldz;
+    const int o0 = q + s * R * p;
+    dp[padx(o0, ps)] = a[0];
     if (m > 1) {
 #pragma unroll
-      for (int k = 1; k < R; ++k) dp[k * s] = ctw<DIR>(a[k], __ldg(twp + (k - 1) * m + p));
+      for (int k = 1; k < R; ++k) dp[padx(o0 + k * s, ps)] = ctw<DIR>(a[k], twp[(k - 1) * m + p]);
     } else {
 #pragma unroll
-      for (int k = 1; k < R; ++k) dp[k * s] = a[k];
+      for (int k = 1; k < R; ++k) dp[padx(o0 + k * s, ps)] = a[k];
     }
   }
 }
@@ -61,7 +66,7 @@ __device__ __forceinline__ void pass_fixed(const cpx *__restrict__ src, cpx *__r
  * output pair (k, r-k) of one butterfly from the symmetric sums, O(r) work per output */
 template <int DIR>
 __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *__restrict__ dst, int T, int ldz, int M,
-                                             const PassDesc &pd, const cpx *__restrict__ tw, int tid, int nthr) {
+                                             const PassDesc &pd, const cpx *__restrict__ tw, int tid, int nthr, int ps) {
   const int r = pd.radix, nb = M / r, s = pd.s, m = pd.m, half = (r + 1) / 2;
   const int per = nb * half;  // work items per sequence: (k in [0, half)) x butterflies, butterflies fastest
   const int total = per * T;
@@ -71,13 +76,14 @@ __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *_
     int t = fast_div(idx, per, pd.mag_per), rem = idx - t * per;
     int k = fast_div(rem, nb, pd.mag_nb), b = rem - k * nb;
     int p = fast_div(b, s, pd.mag_s), q = b - p * s;
-    const cpx *sp = src + t * ldz + b;
-    cpx *dp = dst + t * ldz + q + s * r * p;
-    cpx a0 = sp[0];
+    const cpx *sp = src + t * ldz;
+    cpx *dp = dst + t * ldz;
+    const int o0 = q + s * r * p;
+    cpx a0 = sp[padx(b, ps)];
     if (k == 0) {
       cpx acc = a0;
-      for (int j = 1; j < r; ++j) acc = cadd(acc, sp[j * nb]);
-      dp[0] = acc;
+      for (int j = 1; j < r; ++j) acc = cadd(acc, sp[padx(b + j * nb, ps)]);
+      dp[padx(o0, ps)] = acc;
     } else {
       // X_k = a0 + sum_{j=1}^{half-1} [ c_jk (a_j + a_{r-j}) + DIR*i * s_jk (a_j - a_{r-j}) ],  X_{r-k}: minus sign
       double ar = a0.x, ai = a0.y, br = 0.0, bi = 0.0;
@@ -85,8 +91,8 @@ __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *_
       for (int j = 1; j < half; ++j) {
         jk += k;
         if (jk >= r) jk -= r;
-        cpx w = __ldg(rt + jk);  // (cos, -sin)(2 pi jk / r)
-        cpx u = sp[j * nb], v = sp[(r - j) * nb];
+        cpx w = rt[jk];  // (cos, -sin)(2 pi jk / r)
+        cpx u = sp[padx(b + j * nb, ps)], v = sp[padx(b + (r - j) * nb, ps)];
         double pr = u.x + v.x, pi = u.y + v.y, mr = u.x - v.x, mi = u.y - v.y;
         ar = fma(w.x, pr, ar);
         ai = fma(w.x, pi, ai);
@@ -103,26 +109,28 @@ __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *_
         xc = make_double2(ar + bi, ai - br);
       }
       if (m > 1) {
-        xk = ctw<DIR>(xk, __ldg(twp + (k - 1) * m + p));
-        xc = ctw<DIR>(xc, __ldg(twp + (r - k - 1) * m + p));
+        xk = ctw<DIR>(xk, twp[(k - 1) * m + p]);
+        xc = ctw<DIR>(xc, twp[(r - k - 1) * m + p]);
       }
-      dp[k * s] = xk;
-      dp[(r - k) * s] = xc;
+      dp[padx(o0 + k * s, ps)] = xk;
+      dp[padx(o0 + (r - k) * s, ps)] = xc;
     }
   }
 }
 
 template <int DIR>
-__device__ __forceinline__ void run_passes(cpx *&cur, cpx *&oth, const EngineParams &P, int tid, int nthr) {
+__device__ __forceinline__ void run_passes(cpx *&cur, cpx *&oth, const EngineParams &P, const cpx *__restrict__ tw,
+                                           int tid, int nthr) {
+  const int ps = P.padshift;
   for (int ip = 0; ip < P.nf; ++ip) {
     const PassDesc &pd = P.pass[ip];
     switch (pd.radix) {
-      case 2: pass_fixed<2, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
-      case 3: pass_fixed<3, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
-      case 4: pass_fixed<4, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
-      case 5: pass_fixed<5, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
-      case 8: pass_fixed<8, DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
-      default: pass_generic<DIR>(cur, oth, P.T, P.ldz, P.M, pd, P.tw, tid, nthr); break;
+      case 2: pass_fixed<2, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 3: pass_fixed<3, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 4: pass_fixed<4, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 5: pass_fixed<5, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 8: pass_fixed<8, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      default: pass_generic<DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
     }
     __syncthreads();
     cpx *t = cur;
@@ -369,61 +377,86 @@ __device__ __forceinline__ void post_sequence(int kind, int dir, int n, int M, c
     }                                                                                  \
   }
 
-__global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const EngineParams P) {
+/* complex sequences, software-pipelined: while tile k is transformed, tile k+1 is gathered from global memory into
+ * a second landing buffer with per-thread asynchronous copies (cp.async / LDGSTS), so the long global-load latency
+ * is off the critical path.  Buffers: L[0], L[1] (landing, alternate) and W (ping-pong partner of the passes). */
+__device__ __forceinline__ void c2c_issue_loads(const EngineParams &P, cpx *L, const long long *off_in, int tid, int nthr) {
+  const cpx *in = (const cpx *)P.in;
+  const long long inc_in = P.ain.inc;
+  const int T = P.T, M = P.M, ldz = P.ldz, ps = P.padshift, al = P.aligned16;
+  CFB_TILE_LOOP(T, M, P.ain.lanes_t, P.tx_in_log2, {
+    const long long o = off_in[r];
+    if (o >= 0) {
+      const cpx *p = in + o + e * inc_in;
+      cpx *d = L + r * ldz + padx(e, ps);
+      if (al) cp_async16(d, p);
+      else {
+        cp_async8(d, p);
+        cp_async8((double *)d + 1, (const double *)p + 1);
+      }
+    }
+  })
+  cp_async_commit();
+}
+
+__global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_c2c_kernel(const EngineParams P) {
   CFB_DYN_SMEM(smem_raw);
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int T = P.T, ldz = P.ldz, M = P.M, n = P.n;
-  cpx *zA = (cpx *)smem_raw;
-  cpx *zB = zA + T * ldz;
-  const int rows = (P.kind == K_C2C) ? T : 2 * T;
-  long long *off_in = (long long *)(zB + T * ldz);  // [rows] element offsets of each row, -1 = past the batch
-  long long *off_out = off_in + rows;
-  double *dsum = (double *)(off_out + rows);         // [rows]
-  int *row_lo = (int *)(dsum + rows);                // [rows] index within the inner batch level (four-step twiddle)
-  const long long row0 = (long long)blockIdx.x * rows;
-  for (int r = tid; r < rows; r += nthr) {
-    long long g = row0 + r;
-    off_in[r] = g < P.lot ? batch_off(P.ain, g) : -1;
-    off_out[r] = g < P.lot ? batch_off(P.aout, g) : -1;
-    row_lo[r] = (int)(g % P.aout.nlo);
+  const int T = P.T, ldz = P.ldz, M = P.M;
+  cpx *L0 = (cpx *)smem_raw, *L1 = L0 + T * ldz, *W = L1 + T * ldz;
+  // row tables, three slots: slot (it+1)%3 is written for the next tile while slow threads may still be storing
+  // tile it-1 from slot (it-1)%3
+  long long *off_in = (long long *)(W + T * ldz);  // [3][T]
+  long long *off_out = off_in + 3 * T;             // [3][T]
+  int *row_lo = (int *)(off_out + 3 * T);          // [3][T]
+  cpx *tws = (cpx *)(((uintptr_t)(row_lo + 3 * T) + 15) & ~(uintptr_t)15);
+  const cpx *tw = P.tw;
+  if (P.tw_smem > 0) {
+    for (int i = tid; i < P.tw_smem; i += nthr) tws[i] = __ldg(P.tw + i);
+    tw = tws;
   }
+  auto fill_offsets = [&](long long tile, int slot) {
+    const long long row0 = tile * T;
+    for (int r = tid; r < T; r += nthr) {
+      long long g = row0 + r;
+      const bool ok = tile < P.ntiles && g < P.lot;
+      off_in[slot * T + r] = ok ? batch_off(P.ain, g) : -1;
+      off_out[slot * T + r] = ok ? batch_off(P.aout, g) : -1;
+      row_lo[slot * T + r] = (int)(P.fs_from_hi ? g / P.aout.nlo : g % P.aout.nlo);
+    }
+  };
+  long long tile = blockIdx.x;
+  fill_offsets(tile, 0);
   __syncthreads();
-
-  if (P.kind == K_C2C) {
-    /* ---- load: global -> zA ---- */
-    const cpx *in = (const cpx *)P.in;
-    const long long inc_in = P.ain.inc;
-    const int al = P.aligned16;
-    CFB_TILE_LOOP(T, M, P.ain.lanes_t, P.tx_in_log2, {
-      cpx v = make_double2(0.0, 0.0);
-      const long long o = off_in[r];
-      if (o >= 0) {
-        const cpx *p = in + o + e * inc_in;
-        if (al) v = *p;
-        else {
-          v.x = ((const double *)p)[0];
-          v.y = ((const double *)p)[1];
-        }
-      }
-      zA[r * ldz + e] = v;
-    })
-    __syncthreads();
-    cpx *cur = zA, *oth = zB;
-    if (P.dir < 0) run_passes<-1>(cur, oth, P, tid, nthr);
-    else run_passes<1>(cur, oth, P, tid, nthr);
-    /* ---- store: cur -> global ---- */
+  c2c_issue_loads(P, L0, off_in, tid, nthr);
+  int it = 0;
+  for (; tile < P.ntiles; tile += gridDim.x, ++it) {
+    const int slot = it % 3, nslot = (it + 1) % 3;
+    cpx *L = (it & 1) ? L1 : L0, *Ln = (it & 1) ? L0 : L1;
+    fill_offsets(tile + gridDim.x, nslot);
+    __syncthreads();  // offsets of the next tile are visible; everybody is done with the other landing buffer
+    c2c_issue_loads(P, Ln, off_in + nslot * T, tid, nthr);  // (empty group past the last tile)
+    cp_async_wait<1>();
+    __syncthreads();  // this tile has landed for all threads
+    cpx *cur = L, *oth = W;
+    if (P.dir < 0) run_passes<-1>(cur, oth, P, tw, tid, nthr);
+    else run_passes<1>(cur, oth, P, tw, tid, nthr);
     cpx *out = (cpx *)P.out;
     const long long inc_out = P.aout.inc;
     const double scale = P.scale;
     const cpx *fs = P.fs_tw;
+    const int fs_mask = (1 << P.fs_shift) - 1, ps = P.padshift, al = P.aligned16;
+    const long long *oo = off_out + slot * T;
+    const int *rl = row_lo + slot * T;
     CFB_TILE_LOOP(T, M, P.aout.lanes_t, P.tx_out_log2, {
-      const long long o = off_out[r];
+      const long long o = oo[r];
       if (o >= 0) {
-        cpx v = cur[r * ldz + e];
+        cpx v = cur[r * ldz + padx(e, ps)];
         v.x *= scale;
         v.y *= scale;
-        if (fs) {  // W_n^(lo*e); lo < n2 and e < n1, so lo*e < n = fs_n: no reduction needed
-          cpx w = __ldg(fs + row_lo[r] * e);
+        if (fs) {  // W_n^(j*e), j*e < n: two small L1-resident tables and one product instead of an n-entry gather
+          const int x = rl[r] * e;
+          cpx w = cmul(__ldg(fs + (x & fs_mask)), __ldg(fs + fs_mask + 1 + (x >> P.fs_shift)));
           v = (P.dir < 0) ? cmul(v, w) : cmulc(v, w);
         }
         cpx *p = out + o + e * inc_out;
@@ -434,8 +467,38 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
         }
       }
     })
-    return;
   }
+  cp_async_wait<0>();
+}
+
+__global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const EngineParams P) {
+  CFB_DYN_SMEM(smem_raw);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int T = P.T, ldz = P.ldz, M = P.M, n = P.n, ps = P.padshift;
+  cpx *zA = (cpx *)smem_raw;
+  cpx *zB = zA + T * ldz;
+  const int rows = 2 * T;  // this kernel serves the real families only (complex: engine_c2c_kernel)
+  long long *off_in = (long long *)(zB + T * ldz);  // [rows] element offsets of each row, -1 = past the batch
+  long long *off_out = off_in + rows;
+  double *dsum = (double *)(off_out + rows);         // [rows]
+  int *row_lo = (int *)(dsum + rows);                // [rows] index along the split axis (four-step twiddle)
+  cpx *tws = (cpx *)(((uintptr_t)(row_lo + rows) + 15) & ~(uintptr_t)15);  // [tw_smem] copy of the plan's twiddles
+  const cpx *tw = P.tw;
+  if (P.tw_smem > 0) {
+    for (int i = tid; i < P.tw_smem; i += nthr) tws[i] = __ldg(P.tw + i);
+    tw = tws;
+  }
+  /* persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... */
+  for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+  __syncthreads();  // previous tile's readers of the row tables and buffers are done; twiddle copy is visible
+  const long long row0 = tile * rows;
+  for (int r = tid; r < rows; r += nthr) {
+    long long g = row0 + r;
+    off_in[r] = g < P.lot ? batch_off(P.ain, g) : -1;
+    off_out[r] = g < P.lot ? batch_off(P.aout, g) : -1;
+    row_lo[r] = (int)(P.fs_from_hi ? g / P.aout.nlo : g % P.aout.nlo);
+  }
+  __syncthreads();
 
   /* ---- real kinds: T pairs of sequences.  Real rows live in whichever complex buffer is free, viewed as
    * [2T][ldz] doubles (exactly one complex buffer). ---- */
@@ -468,7 +531,7 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
     __syncthreads();
     cur = zA;
     oth = zB;
-    run_passes<-1>(cur, oth, P, tid, nthr);
+    run_passes<-1>(cur, oth, P, tw, tid, nthr);
     /* split: cur -> half-complex rows in oth */
     double *hs = (double *)oth;
     const int nfq = M / 2 + 1;
@@ -489,7 +552,7 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
     __syncthreads();
     cur = zB;
     oth = zA;
-    run_passes<1>(cur, oth, P, tid, nthr);
+    run_passes<1>(cur, oth, P, tw, tid, nthr);
     /* extract: re/im of cur -> real rows in oth */
     double *us = (double *)oth;
     for (int t = 0; t < T; ++t)
@@ -520,6 +583,7 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
       }
     })
   }
+  }  // tile loop
 }
 
 /* closed forms for the lengths the reference special-cases (costf1_ n=2,3 fftpack.c:6339-6353; sintf1_ n=2

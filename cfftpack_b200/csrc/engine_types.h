@@ -39,6 +39,9 @@ struct EngineParams {
   int ldz;  // row pitch of the complex buffers (odd, >= max(M, n)); real rows use the same pitch in doubles
   int ldx;  // unused (kept for layout stability)
   int tx_in_log2, tx_out_log2;  // loader / storer thread tiling: 2^tx threads walk the contiguous axis
+  int padshift;                 // shared-memory rows get one pad slot every 2^padshift elements (31 = none)
+  int tw_smem;                  // > 0: number of plan twiddles copied to shared memory by each CTA
+  long long ntiles;             // tiles of T sequences (pairs); CTAs are persistent and stride over them
   int aligned16;  // c2c: in and out are 16-byte aligned
   long long lot;  // sequences in the batch
   Addr ain, aout;
@@ -47,8 +50,10 @@ struct EngineParams {
   const cpx *tw;       // twiddles of all passes, forward convention
   const double *trig;  // kind tables (see plan.cpp)
   double scale;        // c2c: factor applied on store
-  const cpx *fs_tw;    // four-step: multiply element e of sequence g by fs_tw[((g % nlo) * e) % fs_n] on store
-  int fs_n;
+  // four-step: element e of row g is multiplied on store by W_n^(j*e), j = the row's index along the split axis
+  // (g % nlo or g / nlo, fs_from_hi).  W_n^x = fs_tw[x & (2^fs_shift - 1)] * fs_tw[2^fs_shift + (x >> fs_shift)]
+  const cpx *fs_tw;
+  int fs_n, fs_shift, fs_from_hi;
   PassDesc pass[CFB_MAXPASS];
 };
 

@@ -51,25 +51,28 @@ int engine_factor(int M, int *radix) {
     M /= 2;
     ++a;
   }
-  // power of two: as many 8s as possible, the remainder as 4s / one 2 (the engine keeps <= 8 points per thread)
+  // power of two: 8s first (the first pass's scattered stores are conflict-free with one pad slot per 8 elements),
+  // then the remainder as 4s / one 2 (the engine keeps <= 8 points per thread)
+  int tail[2], ntail = 0;
   switch (a % 3) {
     case 1:
       if (a >= 4) {
-        radix[nf++] = 4;
-        radix[nf++] = 4;
+        tail[ntail++] = 4;
+        tail[ntail++] = 4;
         a -= 4;
       } else {
-        radix[nf++] = 2;
+        tail[ntail++] = 2;
         a -= 1;
       }
       break;
-    case 2: radix[nf++] = 4; a -= 2; break;
+    case 2: tail[ntail++] = 4; a -= 2; break;
     default: break;
   }
   while (a >= 3) {
     radix[nf++] = 8;
     a -= 3;
   }
+  for (int i = 0; i < ntail; ++i) radix[nf++] = tail[i];
   while (M % 5 == 0) {
     radix[nf++] = 5;
     M /= 5;
@@ -234,8 +237,13 @@ const RootPlan *get_root_plan(int n) {
   if (it != g_root.end()) return it->second;
   RootPlan *pl = new RootPlan();
   pl->n = n;
-  std::vector<cpx> w(n);
-  for (int j = 0; j < n; ++j) unit_root(j, n, &w[j].x, &w[j].y);
+  int shift = 0;
+  while ((1LL << (2 * shift)) < n) ++shift;
+  pl->shift = shift;
+  const int B = 1 << shift, H = (n + B - 1) / B;
+  std::vector<cpx> w((size_t)B + H);
+  for (int j = 0; j < B; ++j) unit_root(j, n, &w[j].x, &w[j].y);
+  for (int j = 0; j < H; ++j) unit_root((long long)j * B, n, &w[B + j].x, &w[B + j].y);
   pl->d_w = upload(w);
   if (!pl->d_w) {
     delete pl;

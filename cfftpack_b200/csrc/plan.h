@@ -28,9 +28,9 @@ struct TrigPlan {
   double *d_trig = nullptr;
 };
 
-/* W_n^j, j < n, for the four-step decomposition of long transforms */
+/* four-step twiddles W_n^x, x < n, as two short tables: d_w[x & (B-1)] * d_w[B + (x >> shift)], B = 2^shift ~ sqrt(n) */
 struct RootPlan {
-  int n = 0;
+  int n = 0, shift = 0;
   cpx *d_w = nullptr;
 };
 

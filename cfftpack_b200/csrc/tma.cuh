@@ -29,6 +29,12 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
 __device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
   bulk_g2s(smem_dst, gsrc, bytes, bar);
 }
+/* Ampere-style per-thread asynchronous copies (LDGSTS): gathers with arbitrary addresses, no register staging */
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 8); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
 #else
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -59,6 +65,17 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 /* same, tagging the lines evict-first in L2: a streamed sequence is read exactly once */
 __device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {

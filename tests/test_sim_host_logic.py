@@ -85,6 +85,9 @@ def test_four_step_long_complex(libs):
         for d in "fb":
             _check(S, O, "cfft", d, 2, n, n, 1)
     _check(S, O, "cfft", "f", 2, 1, 8192, 2)  # interleaved long: pow2 kernel not applicable -> four-step
+    for d in "fb":  # batch-contiguous four-step (rows enumerate the batch index fastest), cfft2f_'s first sweep
+        _check(S, O, "cfft", d, 3, 1, 16384, 3)
+        _check(S, O, "cfft", d, 5, 1, 9000, 7)
 
 
 def test_cfft2(libs):
