@@ -96,7 +96,7 @@ static bool launch_engine(EngineParams &P) {
   // bytes per sequence (c2c: three complex rows -- two landing buffers + the ping-pong partner -- and double-buffered
   // row tables) or per pair (real kinds: two complex rows and the row tables)
   const size_t per = real ? (size_t)P.ldz * 32 + 64 : (size_t)P.ldz * 48 + 64;
-  const size_t fixed = 64 + (size_t)P.tw_smem * sizeof(cpx);
+  const size_t fixed = 64 + (size_t)(P.tw_smem + P.fs_smem) * sizeof(cpx);
   const long long units = real ? (P.lot + 1) / 2 : P.lot;
   if (per + fixed > SMEM_MAX) {
     set_error("length %d does not fit one CTA (%zu bytes)", P.n, per + fixed);
@@ -134,6 +134,55 @@ static bool launch_engine(EngineParams &P) {
   return cuda_ok(cudaGetLastError(), "engine kernel launch");
 }
 
+/* long power-of-two transforms: both sweeps of the four-step split run in the register tile kernel (pow2.cuh) */
+static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c) {
+  const int n1 = 1 << a1, n2 = 1 << a2;
+  const RootPlan *rp = get_root_plan(n);
+  if (!rp) return false;
+  cpx *scr = (cpx *)scratch_get(0, (size_t)lot * n * sizeof(cpx));
+  if (!scr) return false;
+  const long long ainc = inc < 0 ? -inc : inc, ajump = jump < 0 ? -jump : jump;
+  const bool batch_fast = ajump < ainc && lot > 1;
+  TileParams P;
+  memset(&P, 0, sizeof(P));
+  // step 1: rows (m, j2), transform over j1 (length n1), twiddle W_n^(j2*k1) on store
+  P.in = c;
+  P.out = scr;
+  P.lot = lot * n2;
+  P.scale = 1.0;
+  P.fs = rp->d_w;
+  P.fs_shift = rp->shift;
+  P.fs_count = (1 << rp->shift) + (n + (1 << rp->shift) - 1) / (1 << rp->shift);
+  if (!batch_fast) {  // row g = m*n2 + j2 (j2 fast); scratch S[m][k1][j2]
+    P.ain = make_addr((long long)n2 * inc, inc, jump, n2);
+    P.aout = make_addr(n2, 1, n, n2);
+    P.fs_from_hi = 0;
+  } else {  // row g = j2*lot + m (m fast); scratch S[k1][j2][m]
+    P.ain = make_addr((long long)n2 * inc, jump, inc, lot);
+    P.aout = make_addr((long long)n2 * lot, 1, lot, lot);
+    P.fs_from_hi = 1;
+  }
+  P.in_staged = 0;
+  if (!pow2_tile_launch(a1, dir, P)) return false;
+  // step 2: rows (m, k1), transform over j2 (length n2), output element k2 goes to index k1 + n1*k2
+  P.in = scr;
+  P.out = c;
+  P.lot = lot * n1;
+  P.scale = dir < 0 ? 1.0 / (double)n : 1.0;
+  P.fs = nullptr;
+  P.fs_count = 0;
+  if (!batch_fast) {  // row g = m*n1 + k1: scratch rows are contiguous along j2 -> staged load
+    P.ain = make_addr(1, n2, n, n1);
+    P.aout = make_addr((long long)n1 * inc, inc, jump, n1);
+    P.in_staged = 1;
+  } else {  // row g = k1*lot + m
+    P.ain = make_addr(lot, 1, (long long)n2 * lot, lot);
+    P.aout = make_addr((long long)n1 * inc, jump, inc, lot);
+    P.in_staged = 0;
+  }
+  return pow2_tile_launch(a2, dir, P);
+}
+
 bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void *c) {
   if (n <= 1 || lot <= 0) return true;
   const int aligned = (((uintptr_t)c) & 15) == 0;
@@ -162,6 +211,12 @@ bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void 
     return launch_engine(P);
   }
   /* four-step: x[j1*n2 + j2] -> (FFT over j1) * W_n^{j2 k1} -> scratch[k1*n2 + j2] -> (FFT over j2) -> X[k1 + n1 k2] */
+  if (aligned && (n & (n - 1)) == 0) {
+    int a = 0;
+    while ((1 << a) < n) ++a;
+    const int a1 = a / 2, a2 = a - a1;
+    if (a1 >= pow2_tile_min_log2() && a2 <= pow2_tile_max_log2()) return run_c2c_pow2_four_step(n, a1, a2, lot, inc, jump, dir, (cpx *)c);
+  }
   const int n1 = four_step_split(n, engine_max_c2c());
   if (n1 <= 1) {
     set_error("length %d has a prime factor too large for the four-step path", n);
@@ -182,6 +237,10 @@ bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void 
   P.fs_tw = rp->d_w;
   P.fs_n = n;
   P.fs_shift = rp->shift;
+  {
+    const int entries = (1 << rp->shift) + (n + (1 << rp->shift) - 1) / (1 << rp->shift);
+    P.fs_smem = entries <= CFB_FS_SMEM_MAX ? entries : 0;
+  }
   // step 1: rows (m, j2), transform over j1, twiddle W_n^(j2*k1) on store
   fill_passes(P, p1);
   P.n = n1;
@@ -215,6 +274,7 @@ bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void 
   P.scale = dir < 0 ? 1.0 / (double)n : 1.0;
   P.fs_tw = nullptr;
   P.fs_n = 0;
+  P.fs_smem = 0;
   return launch_engine(P);
 }
 

@@ -379,25 +379,46 @@ __device__ __forceinline__ void post_sequence(int kind, int dir, int n, int M, c
 
 /* complex sequences, software-pipelined: while tile k is transformed, tile k+1 is gathered from global memory into
  * a second landing buffer with per-thread asynchronous copies (cp.async / LDGSTS), so the long global-load latency
- * is off the critical path.  Buffers: L[0], L[1] (landing, alternate) and W (ping-pong partner of the passes). */
+ * is off the critical path.  Buffers: L[0], L[1] (landing, alternate) and W (ping-pong partner of the passes).
+ * Loader and storer keep a running global pointer per thread (no per-element 64-bit multiplies or table reads). */
+struct TileWalk {
+  int rs, rn, es, en;  // this thread's first row / row step, first element / element step
+};
+__device__ __forceinline__ TileWalk tile_walk(int tid, int nthr, int txl, int lanes_t) {
+  const int tx = tid & ((1 << txl) - 1), ty = tid >> txl, nx = 1 << txl, ny = nthr >> txl;
+  TileWalk w;
+  if (lanes_t) {  // consecutive threads walk the rows (batch axis contiguous in memory)
+    w.rs = tx; w.rn = nx; w.es = ty; w.en = ny;
+  } else {        // consecutive threads walk the elements
+    w.rs = ty; w.rn = ny; w.es = tx; w.en = nx;
+  }
+  return w;
+}
+
 __device__ __forceinline__ void c2c_issue_loads(const EngineParams &P, cpx *L, const long long *off_in, int tid, int nthr) {
   const cpx *in = (const cpx *)P.in;
-  const long long inc_in = P.ain.inc;
   const int T = P.T, M = P.M, ldz = P.ldz, ps = P.padshift, al = P.aligned16;
-  CFB_TILE_LOOP(T, M, P.ain.lanes_t, P.tx_in_log2, {
+  const TileWalk w = tile_walk(tid, nthr, P.tx_in_log2, P.ain.lanes_t);
+  const long long step = (long long)w.en * P.ain.inc;
+  for (int r = w.rs; r < T; r += w.rn) {
     const long long o = off_in[r];
-    if (o >= 0) {
-      const cpx *p = in + o + e * inc_in;
-      cpx *d = L + r * ldz + padx(e, ps);
-      if (al) cp_async16(d, p);
-      else {
+    if (o < 0) continue;
+    const cpx *p = in + o + (long long)w.es * P.ain.inc;
+    cpx *row = L + r * ldz;
+    if (al) {
+      for (int e = w.es; e < M; e += w.en, p += step) cp_async16(row + padx(e, ps), p);
+    } else {
+      for (int e = w.es; e < M; e += w.en, p += step) {
+        cpx *d = row + padx(e, ps);
         cp_async8(d, p);
         cp_async8((double *)d + 1, (const double *)p + 1);
       }
     }
-  })
+  }
   cp_async_commit();
 }
+
+#define CFB_FS_SMEM_MAX 512  /* four-step twiddle tables up to this many entries are kept in shared memory */
 
 __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_c2c_kernel(const EngineParams P) {
   CFB_DYN_SMEM(smem_raw);
@@ -410,10 +431,16 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_c2c_kernel(const
   long long *off_out = off_in + 3 * T;             // [3][T]
   int *row_lo = (int *)(off_out + 3 * T);          // [3][T]
   cpx *tws = (cpx *)(((uintptr_t)(row_lo + 3 * T) + 15) & ~(uintptr_t)15);
+  cpx *fss = tws + P.tw_smem;
   const cpx *tw = P.tw;
   if (P.tw_smem > 0) {
     for (int i = tid; i < P.tw_smem; i += nthr) tws[i] = __ldg(P.tw + i);
     tw = tws;
+  }
+  const cpx *fs = P.fs_tw;
+  if (fs && P.fs_smem > 0) {
+    for (int i = tid; i < P.fs_smem; i += nthr) fss[i] = __ldg(P.fs_tw + i);
+    fs = fss;
   }
   auto fill_offsets = [&](long long tile, int slot) {
     const long long row0 = tile * T;
@@ -429,6 +456,10 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_c2c_kernel(const
   fill_offsets(tile, 0);
   __syncthreads();
   c2c_issue_loads(P, L0, off_in, tid, nthr);
+  const TileWalk ws = tile_walk(tid, nthr, P.tx_out_log2, P.aout.lanes_t);
+  const long long ostep = (long long)ws.en * P.aout.inc;
+  const int fs_mask = (1 << P.fs_shift) - 1, fs_shift = P.fs_shift, ps = P.padshift, al = P.aligned16;
+  const double scale = P.scale;
   int it = 0;
   for (; tile < P.ntiles; tile += gridDim.x, ++it) {
     const int slot = it % 3, nslot = (it + 1) % 3;
@@ -441,32 +472,32 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_c2c_kernel(const
     cpx *cur = L, *oth = W;
     if (P.dir < 0) run_passes<-1>(cur, oth, P, tw, tid, nthr);
     else run_passes<1>(cur, oth, P, tw, tid, nthr);
-    cpx *out = (cpx *)P.out;
-    const long long inc_out = P.aout.inc;
-    const double scale = P.scale;
-    const cpx *fs = P.fs_tw;
-    const int fs_mask = (1 << P.fs_shift) - 1, ps = P.padshift, al = P.aligned16;
+    /* ---- store: cur -> global (scale, four-step twiddle) ---- */
     const long long *oo = off_out + slot * T;
     const int *rl = row_lo + slot * T;
-    CFB_TILE_LOOP(T, M, P.aout.lanes_t, P.tx_out_log2, {
+    for (int r = ws.rs; r < T; r += ws.rn) {
       const long long o = oo[r];
-      if (o >= 0) {
-        cpx v = cur[r * ldz + padx(e, ps)];
+      if (o < 0) continue;
+      cpx *p = (cpx *)P.out + o + (long long)ws.es * P.aout.inc;
+      const cpx *row = cur + r * ldz;
+      const int j = rl[r];
+      int x = j * ws.es;
+      const int xstep = j * ws.en;
+      for (int e = ws.es; e < M; e += ws.en, p += ostep, x += xstep) {
+        cpx v = row[padx(e, ps)];
         v.x *= scale;
         v.y *= scale;
-        if (fs) {  // W_n^(j*e), j*e < n: two small L1-resident tables and one product instead of an n-entry gather
-          const int x = rl[r] * e;
-          cpx w = cmul(__ldg(fs + (x & fs_mask)), __ldg(fs + fs_mask + 1 + (x >> P.fs_shift)));
+        if (fs) {  // W_n^(j*e), j*e < n: two short tables and one product instead of an n-entry gather
+          const cpx w = cmul(fs[x & fs_mask], fs[fs_mask + 1 + (x >> fs_shift)]);
           v = (P.dir < 0) ? cmul(v, w) : cmulc(v, w);
         }
-        cpx *p = out + o + e * inc_out;
         if (al) *p = v;
         else {
           ((double *)p)[0] = v.x;
           ((double *)p)[1] = v.y;
         }
       }
-    })
+    }
   }
   cp_async_wait<0>();
 }

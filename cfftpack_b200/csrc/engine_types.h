@@ -54,6 +54,7 @@ struct EngineParams {
   // (g % nlo or g / nlo, fs_from_hi).  W_n^x = fs_tw[x & (2^fs_shift - 1)] * fs_tw[2^fs_shift + (x >> fs_shift)]
   const cpx *fs_tw;
   int fs_n, fs_shift, fs_from_hi;
+  int fs_smem;  // > 0: entries of fs_tw copied to shared memory by each CTA
   PassDesc pass[CFB_MAXPASS];
 };
 

@@ -12,6 +12,7 @@
 namespace cfb {
 
 namespace {
+const size_t SMEM_LIMIT = 227 * 1024;
 std::mutex g_mu;
 std::map<std::tuple<int, int, int, int>, cpx *> g_tw;  // (device, log2n, lp, tw) -> table
 
@@ -203,6 +204,30 @@ bool launch_r2c(long long lot, long long jump, double *r) {
   return launch_r2c_stream<Pow2Cfg<LOG2N>, StreamMinB<LOG2N>::value, DIR>(lot, jump, r);
 }
 
+template <int LOG2N, int DIR>
+bool launch_tile(TileParams &P) {
+  typedef Pow2Cfg<LOG2N, 4, 0> C;
+  P.tw = pow2_table<C>();
+  if (!P.tw) return false;
+  static std::once_flag once;
+  static bool ok = true;
+  auto kern = pow2_tile_kernel<C, DIR>;
+  if (!set_smem_once(kern, SMEM_LIMIT, once, ok)) return false;
+  const size_t smem = TileSmem<C>::bytes(P.fs_count);
+  if (smem > SMEM_LIMIT) {
+    set_error("pow2_tile_kernel: %zu bytes of shared memory", smem);
+    return false;
+  }
+  const long long grid = (P.lot + C::TPB - 1) / C::TPB;
+  if (grid > 2147483647LL) {
+    set_error("batch too large");
+    return false;
+  }
+  CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, smem, current_stream(), P);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "pow2_tile_kernel launch");
+}
+
 int ilog2_exact(int n) {
   int l = 0;
   while ((1 << l) < n) ++l;
@@ -233,6 +258,21 @@ bool pow2_r2c_supported(int n, long long inc, long long jump, int) {
     case 13: return dir < 0 ? FN<13, -1>(__VA_ARGS__) : FN<13, 1>(__VA_ARGS__); \
     default: break;                                                   \
   }
+
+int pow2_tile_min_log2() { return 6; }
+int pow2_tile_max_log2() { return 10; }
+bool pow2_tile_launch(int log2n, int dir, TileParams &P) {
+  switch (log2n) {
+    case 6: return dir < 0 ? launch_tile<6, -1>(P) : launch_tile<6, 1>(P);
+    case 7: return dir < 0 ? launch_tile<7, -1>(P) : launch_tile<7, 1>(P);
+    case 8: return dir < 0 ? launch_tile<8, -1>(P) : launch_tile<8, 1>(P);
+    case 9: return dir < 0 ? launch_tile<9, -1>(P) : launch_tile<9, 1>(P);
+    case 10: return dir < 0 ? launch_tile<10, -1>(P) : launch_tile<10, 1>(P);
+    default: break;
+  }
+  set_error("pow2_tile_launch: unsupported row length 2^%d", log2n);
+  return false;
+}
 
 bool pow2_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c) {
   CFB_POW2_CASES(launch_c2c, lot, jump, c)

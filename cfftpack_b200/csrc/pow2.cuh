@@ -20,6 +20,7 @@
 #include <mutex>
 
 #include "butterfly.cuh"
+#include "engine_types.h"
 #include "internal.h"
 #include "tma.cuh"
 
@@ -472,11 +473,117 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
   }
 }
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Tile kernel for the four-step decomposition of long power-of-two transforms (cfft2f_ 16384^2, cfftmf_ N >= 2^13
+ * with strides): one CTA transforms TPB short sequences ("rows", N = 64..1024) whose elements are strided in
+ * memory.  Threads are laid out rows-fastest, so for the layouts the four-step driver produces (the row index is the
+ * contiguous axis) every warp-wide load/store of one register slot covers consecutive rows = full 128-byte runs.
+ * The one side of the decomposition whose rows are contiguous along the ELEMENT axis is staged through the
+ * shared-memory tile instead (that is where the transposition of the four-step algorithm happens).
+ * Twiddles W_n^(j e) of the split are applied on store from two short shared-memory tables.
+ * --------------------------------------------------------------------------------------------------------- */
+struct TileParams {
+  const cpx *in;
+  cpx *out;
+  Addr ain, aout;
+  long long lot;  // rows
+  double scale;
+  const cpx *tw;  // pow2_table of the row length
+  const cpx *fs;  // split twiddle tables of the long length (nullptr: none)
+  int fs_shift, fs_from_hi, fs_count;
+  int in_staged;  // 1: rows are contiguous along the element axis on the input side
+};
+
+template <class C>
+struct TileSmem {
+  static constexpr int PITCH = C::TILE | 1;  // odd pitch: rows-fastest threads hit different banks
+  static constexpr size_t TILE_BYTES = (size_t)C::TPB * PITCH * sizeof(cpx);
+  static constexpr size_t bytes(int fs_count) { return TILE_BYTES + (size_t)C::TPB * 8 + (size_t)fs_count * sizeof(cpx) + 16; }
+};
+
+__device__ __forceinline__ long long tile_batch_off(const Addr &a, long long g) {
+  long long hi = g / a.nlo, lo = g - hi * a.nlo;
+  return hi * a.jump_hi + lo * a.jump_lo;
+}
+
+template <class C, int DIR>
+__global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_kernel(const TileParams P) {
+  CFB_DYN_SMEM(smem_raw);
+  constexpr int N = C::N, PP = C::P, NT = C::NT, TPB = C::TPB, LP = C::LP, PITCH = TileSmem<C>::PITCH;
+  cpx *tile = (cpx *)smem_raw;
+  long long *rowoff = (long long *)(smem_raw + TileSmem<C>::TILE_BYTES);
+  cpx *fss = (cpx *)(smem_raw + TileSmem<C>::TILE_BYTES + (size_t)TPB * 8);
+  const int tid = threadIdx.x, tl = tid % TPB, t = tid / TPB;
+  const long long g = (long long)blockIdx.x * TPB + tl;
+  const bool live = g < P.lot;
+  const long long oin = live ? tile_batch_off(P.ain, g) : 0, oout = live ? tile_batch_off(P.aout, g) : 0;
+  for (int i = tid; i < P.fs_count; i += C::THREADS) fss[i] = __ldg(P.fs + i);
+  cpx *sm = tile + (size_t)tl * PITCH;
+  cpx a[PP];
+  if (!P.in_staged) {
+    const cpx *x = P.in + oin + (long long)t * P.ain.inc;
+    const long long st = (long long)NT * P.ain.inc;
+#pragma unroll
+    for (int i = 0; i < PP; ++i) a[i] = live ? x[i * st] : make_double2(0.0, 0.0);
+    if (P.fs_count > 0) __syncthreads();  // twiddle tables visible
+  } else {
+    // rows contiguous along the element axis: cooperative row-major loads into the tile, then pick up registers
+    if (t == 0) rowoff[tl] = live ? oin : -1;
+    __syncthreads();
+    constexpr int TOTAL = TPB * N;
+    const long long inc = P.ain.inc;
+#pragma unroll 1
+    for (int base = 0; base < TOTAL; base += 4 * C::THREADS) {
+      cpx v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * C::THREADS + tid;
+        const int r = idx / N, e = idx % N;
+        const long long o = idx < TOTAL ? rowoff[r] : -1;
+        v[u] = o >= 0 ? P.in[o + e * inc] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * C::THREADS + tid;
+        const int r = idx / N, e = idx % N;
+        if (idx < TOTAL) tile[(size_t)r * PITCH + pad<LP>(e)] = v[u];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PP; ++i) a[i] = sm[pad<LP>(t + NT * i)];
+    __syncthreads();
+  }
+  pow2_core<C, DIR>(a, sm, t, P.tw);
+  if (live) {
+    cpx *y = P.out + oout + (long long)t * P.aout.inc;
+    const long long st = (long long)NT * P.aout.inc;
+    const double scale = P.scale;
+    if (P.fs_count > 0) {
+      const int j = (int)(P.fs_from_hi ? g / P.aout.nlo : g % P.aout.nlo);
+      const int mask = (1 << P.fs_shift) - 1, sh = P.fs_shift;
+#pragma unroll
+      for (int i = 0; i < PP; ++i) {
+        const int x = j * (t + NT * i);  // < long length
+        const cpx w = cmul(fss[x & mask], fss[mask + 1 + (x >> sh)]);
+        y[i * st] = ctw<DIR>(make_double2(a[i].x * scale, a[i].y * scale), w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < PP; ++i) y[i * st] = make_double2(a[i].x * scale, a[i].y * scale);
+    }
+  }
+}
+
 /* ---- host side ---- */
 bool pow2_c2c_supported(int n, long long inc, long long jump, int aligned16);
 bool pow2_r2c_supported(int n, long long inc, long long jump, int aligned16);
 bool pow2_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c);
 bool pow2_r2c_launch(int n, long long lot, long long jump, int dir, double *r);
+/* four-step rows: log2 of the row length must be within [pow2_tile_min_log2, pow2_tile_max_log2] */
+int pow2_tile_min_log2();
+int pow2_tile_max_log2();
+bool pow2_tile_launch(int log2n, int dir, TileParams &P);
 
 }  // namespace cfb
 #endif
