@@ -22,7 +22,7 @@ static const size_t SMEM_MAX = 227 * 1024;      // opt-in limit per CTA on sm_10
 static const size_t SMEM_TARGET = 72 * 1024;    // aim: three CTAs per SM for the streaming kernels
 
 int engine_max_c2c() { return (int)((SMEM_MAX - 1024) / 48 * 8 / 9) - 2; }
-int engine_max_real() { return (int)((SMEM_MAX - 1024) / 32) - 4; }
+int engine_max_real() { return (int)((SMEM_MAX - 1024) / 48) - 4; }
 
 static bool engine_attr_once() {
   static std::once_flag once;
@@ -95,7 +95,7 @@ static bool launch_engine(EngineParams &P) {
   P.ldx = 0;
   // bytes per sequence (c2c: three complex rows -- two landing buffers + the ping-pong partner -- and double-buffered
   // row tables) or per pair (real kinds: two complex rows and the row tables)
-  const size_t per = real ? (size_t)P.ldz * 32 + 64 : (size_t)P.ldz * 48 + 64;
+  const size_t per = real ? (size_t)P.ldz * 48 + 112 : (size_t)P.ldz * 48 + 64;
   const size_t fixed = 64 + (size_t)(P.tw_smem + P.fs_smem) * sizeof(cpx);
   const long long units = real ? (P.lot + 1) / 2 : P.lot;
   if (per + fixed > SMEM_MAX) {

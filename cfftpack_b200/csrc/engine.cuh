@@ -271,15 +271,16 @@ __device__ __forceinline__ void pre_backward_core(int kind, int n, const double 
                                                   int lane) {
   if (kind == K_RFFT) {
     for (int j = lane; j < n; j += 32) h[j] = x[j];
-  } else {  // cosqb1_ pre (fftpack.c:5604-5616)
+  } else {  // cosqb1_ pre (fftpack.c:5604-5616); sinqb1_ first negates the odd entries (fftpack.c:14160-14166)
+    const double so = (kind == K_SINQ) ? -1.0 : 1.0;
     for (int i0 = 2 + 2 * lane; i0 < n; i0 += 64) {
-      double a = x[i0 - 1], b = x[i0];
+      double a = so * x[i0 - 1], b = x[i0];
       h[i0 - 1] = 0.5 * (a + b);
       h[i0] = 0.5 * (a - b);
     }
     if (lane == 0) {
       h[0] = 0.5 * x[0];
-      if (!(n & 1)) h[n - 1] = 0.5 * x[n - 1];
+      if (!(n & 1)) h[n - 1] = 0.5 * so * x[n - 1];
     }
   }
 }
@@ -502,119 +503,135 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_c2c_kernel(const
   cp_async_wait<0>();
 }
 
+/* real families (rfft / cost / sint / cosq / sinq), T pairs of sequences per tile, software-pipelined like the
+ * complex kernel: the rows of tile k+1 are gathered with 8-byte cp.async while tile k is transformed.
+ * Buffers (each T*ldz complex = 2T rows of ldz doubles): B0, B1 alternate as landing buffer; the landing buffer of the
+ * current tile becomes the ping-pong partner of A once the pre-processing has consumed the rows. */
+__device__ __forceinline__ void real_issue_loads(const EngineParams &P, double *rowsL, const long long *off_in, int tid,
+                                                 int nthr) {
+  const double *in = (const double *)P.in;
+  const int rows = 2 * P.T, n = P.n, ldz = P.ldz;
+  const bool rev = (P.kind == K_SINQ && P.dir < 0);  // sinqf1_ reverses the sequence first (fftpack.c:14247-14256)
+  const TileWalk w = tile_walk(tid, nthr, P.tx_in_log2, P.ain.lanes_t);
+  const long long step = (long long)w.en * P.ain.inc;
+  for (int r = w.rs; r < rows; r += w.rn) {
+    const long long o = off_in[r];
+    double *row = rowsL + r * ldz;
+    if (o < 0) {  // a missing partner row must be exactly zero: it shares a complex transform with a live row
+      for (int e = w.es; e < n; e += w.en) row[e] = 0.0;
+      continue;
+    }
+    const double *p = in + o + (long long)w.es * P.ain.inc;
+    for (int e = w.es; e < n; e += w.en, p += step) cp_async8(row + (rev ? n - 1 - e : e), p);
+  }
+  cp_async_commit();
+}
+
 __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const EngineParams P) {
   CFB_DYN_SMEM(smem_raw);
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int T = P.T, ldz = P.ldz, M = P.M, n = P.n, ps = P.padshift;
-  cpx *zA = (cpx *)smem_raw;
-  cpx *zB = zA + T * ldz;
-  const int rows = 2 * T;  // this kernel serves the real families only (complex: engine_c2c_kernel)
-  long long *off_in = (long long *)(zB + T * ldz);  // [rows] element offsets of each row, -1 = past the batch
-  long long *off_out = off_in + rows;
-  double *dsum = (double *)(off_out + rows);         // [rows]
-  int *row_lo = (int *)(dsum + rows);                // [rows] index along the split axis (four-step twiddle)
-  cpx *tws = (cpx *)(((uintptr_t)(row_lo + rows) + 15) & ~(uintptr_t)15);  // [tw_smem] copy of the plan's twiddles
+  const int T = P.T, ldz = P.ldz, M = P.M, n = P.n;
+  cpx *B0 = (cpx *)smem_raw, *B1 = B0 + T * ldz, *A = B1 + T * ldz;
+  const int rows = 2 * T;
+  long long *off_in = (long long *)(A + T * ldz);  // [3][rows]
+  long long *off_out = off_in + 3 * rows;           // [3][rows]
+  double *dsum = (double *)(off_out + 3 * rows);    // [rows]
+  cpx *tws = (cpx *)(((uintptr_t)(dsum + rows) + 15) & ~(uintptr_t)15);
   const cpx *tw = P.tw;
   if (P.tw_smem > 0) {
     for (int i = tid; i < P.tw_smem; i += nthr) tws[i] = __ldg(P.tw + i);
     tw = tws;
   }
-  /* persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... */
-  for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-  __syncthreads();  // previous tile's readers of the row tables and buffers are done; twiddle copy is visible
-  const long long row0 = tile * rows;
-  for (int r = tid; r < rows; r += nthr) {
-    long long g = row0 + r;
-    off_in[r] = g < P.lot ? batch_off(P.ain, g) : -1;
-    off_out[r] = g < P.lot ? batch_off(P.aout, g) : -1;
-    row_lo[r] = (int)(P.fs_from_hi ? g / P.aout.nlo : g % P.aout.nlo);
-  }
-  __syncthreads();
-
-  /* ---- real kinds: T pairs of sequences.  Real rows live in whichever complex buffer is free, viewed as
-   * [2T][ldz] doubles (exactly one complex buffer). ---- */
+  auto fill_offsets = [&](long long tile, int slot) {
+    const long long row0 = tile * rows;
+    for (int r = tid; r < rows; r += nthr) {
+      long long g = row0 + r;
+      const bool ok = tile < P.ntiles && g < P.lot;
+      off_in[slot * rows + r] = ok ? batch_off(P.ain, g) : -1;
+      off_out[slot * rows + r] = ok ? batch_off(P.aout, g) : -1;
+    }
+  };
   const int kind = P.kind, dir = P.dir;
   const bool fwd_core = !((kind == K_RFFT || kind == K_COSQ || kind == K_SINQ) && dir > 0);
   const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
-  double *rowsB = (double *)zB, *rowsA = (double *)zA;
-  {
-    /* load: global -> real rows in zB.  sinq reverses the sequence (forward) or flips odd entries (backward),
-     * sinqf1_/sinqb1_ fftpack.c:14247-14266 */
-    const double *in = (const double *)P.in;
-    const long long inc_in = P.ain.inc;
-    CFB_TILE_LOOP(rows, n, P.ain.lanes_t, P.tx_in_log2, {
-      const long long o = off_in[r];
-      double v = 0.0;
-      if (o >= 0) v = in[o + e * inc_in];
-      int ed = e;
-      if (kind == K_SINQ) {
-        if (dir < 0) ed = n - 1 - e;
-        else if (e & 1) v = -v;
-      }
-      rowsB[r * ldz + ed] = v;
-    })
-  }
+  const TileWalk ws = tile_walk(tid, nthr, P.tx_out_log2, P.aout.lanes_t);
+  const long long ostep = (long long)ws.en * P.aout.inc;
+  long long tile = blockIdx.x;
+  fill_offsets(tile, 0);
   __syncthreads();
-  cpx *cur, *oth;
-  if (fwd_core) {
-    for (int r = warp; r < rows; r += nwarp)
-      pre_forward_core(kind, dir, n, M, rowsB + r * ldz, (double *)(zA + (r >> 1) * ldz) + (r & 1), P.trig, dsum + r, lane);
-    __syncthreads();
-    cur = zA;
-    oth = zB;
-    run_passes<-1>(cur, oth, P, tw, tid, nthr);
-    /* split: cur -> half-complex rows in oth */
-    double *hs = (double *)oth;
-    const int nfq = M / 2 + 1;
-    for (int t = 0; t < T; ++t)
-      for (int f = tid; f < nfq; f += nthr) split_pair(cur + t * ldz, hs + (2 * t) * ldz, hs + (2 * t + 1) * ldz, M, f);
-    __syncthreads();
-    /* post: half-complex rows (oth) -> result rows (cur, no longer needed) */
-    double *ys = (double *)cur;
-    for (int r = warp; r < rows; r += nwarp) post_sequence(kind, dir, n, M, hs + r * ldz, ys + r * ldz, P.trig, dsum[r], lane);
-    __syncthreads();
-    rowsA = ys;
-  } else {
-    for (int r = warp; r < rows; r += nwarp) pre_backward_core(kind, n, rowsB + r * ldz, rowsA + r * ldz, lane);
-    __syncthreads();
-    const int nfq = M / 2 + 1;
-    for (int t = 0; t < T; ++t)
-      for (int f = tid; f < nfq; f += nthr) build_pair(zB + t * ldz, rowsA + (2 * t) * ldz, rowsA + (2 * t + 1) * ldz, M, f);
-    __syncthreads();
-    cur = zB;
-    oth = zA;
-    run_passes<1>(cur, oth, P, tw, tid, nthr);
-    /* extract: re/im of cur -> real rows in oth */
-    double *us = (double *)oth;
-    for (int t = 0; t < T; ++t)
-      for (int e = tid; e < M; e += nthr) {
-        cpx v = cur[t * ldz + e];
-        us[(2 * t) * ldz + e] = v.x;
-        us[(2 * t + 1) * ldz + e] = v.y;
-      }
-    __syncthreads();
-    double *ys = (double *)cur;
-    for (int r = warp; r < rows; r += nwarp) post_sequence(kind, dir, n, M, us + r * ldz, ys + r * ldz, P.trig, 0.0, lane);
-    __syncthreads();
-    rowsA = ys;
-  }
-  {
-    double *out = (double *)P.out;
-    const long long inc_out = P.aout.inc;
-    CFB_TILE_LOOP(rows, n, P.aout.lanes_t, P.tx_out_log2, {
-      const long long o = off_out[r];
-      if (o >= 0) {
-        int es = e;
-        double sg = 1.0;
-        if (kind == K_SINQ) {
-          if (dir < 0) sg = (e & 1) ? -1.0 : 1.0;
-          else es = n - 1 - e;
+  real_issue_loads(P, (double *)B0, off_in, tid, nthr);
+  int it = 0;
+  for (; tile < P.ntiles; tile += gridDim.x, ++it) {
+    const int slot = it % 3, nslot = (it + 1) % 3;
+    cpx *zB = (it & 1) ? B1 : B0, *Bn = (it & 1) ? B0 : B1;
+    fill_offsets(tile + gridDim.x, nslot);
+    __syncthreads();  // next offsets visible; the previous tile's storers are done with the other landing buffer
+    real_issue_loads(P, (double *)Bn, off_in + nslot * rows, tid, nthr);
+    cp_async_wait<1>();
+    __syncthreads();  // rows of this tile have landed
+    double *rowsB = (double *)zB, *rowsA = (double *)A;
+    cpx *cur, *oth;
+    double *ys;
+    if (fwd_core) {
+      for (int r = warp; r < rows; r += nwarp)
+        pre_forward_core(kind, dir, n, M, rowsB + r * ldz, (double *)(A + (r >> 1) * ldz) + (r & 1), P.trig, dsum + r, lane);
+      __syncthreads();
+      cur = A;
+      oth = zB;
+      run_passes<-1>(cur, oth, P, tw, tid, nthr);
+      /* split: cur -> half-complex rows in oth */
+      double *hs = (double *)oth;
+      const int nfq = M / 2 + 1;
+      for (int t = 0; t < T; ++t)
+        for (int f = tid; f < nfq; f += nthr) split_pair(cur + t * ldz, hs + (2 * t) * ldz, hs + (2 * t + 1) * ldz, M, f);
+      __syncthreads();
+      /* post: half-complex rows (oth) -> result rows (cur, no longer needed) */
+      ys = (double *)cur;
+      for (int r = warp; r < rows; r += nwarp) post_sequence(kind, dir, n, M, hs + r * ldz, ys + r * ldz, P.trig, dsum[r], lane);
+    } else {
+      for (int r = warp; r < rows; r += nwarp) pre_backward_core(kind, n, rowsB + r * ldz, rowsA + r * ldz, lane);
+      __syncthreads();
+      const int nfq = M / 2 + 1;
+      for (int t = 0; t < T; ++t)
+        for (int f = tid; f < nfq; f += nthr) build_pair(zB + t * ldz, rowsA + (2 * t) * ldz, rowsA + (2 * t + 1) * ldz, M, f);
+      __syncthreads();
+      cur = zB;
+      oth = A;
+      run_passes<1>(cur, oth, P, tw, tid, nthr);
+      /* extract: re/im of cur -> real rows in oth */
+      double *us = (double *)oth;
+      for (int t = 0; t < T; ++t)
+        for (int e = tid; e < M; e += nthr) {
+          cpx v = cur[t * ldz + e];
+          us[(2 * t) * ldz + e] = v.x;
+          us[(2 * t + 1) * ldz + e] = v.y;
         }
-        out[o + e * inc_out] = sg * rowsA[r * ldz + es];
+      __syncthreads();
+      ys = (double *)cur;
+      for (int r = warp; r < rows; r += nwarp) post_sequence(kind, dir, n, M, us + r * ldz, ys + r * ldz, P.trig, 0.0, lane);
+    }
+    __syncthreads();
+    /* store: result rows -> global.  sinq: forward negates the odd entries, backward reverses (fftpack.c:14257-14266) */
+    {
+      double *out = (double *)P.out;
+      const long long *oo = off_out + slot * rows;
+      const bool neg_odd = (kind == K_SINQ && dir < 0), rev = (kind == K_SINQ && dir > 0);
+      for (int r = ws.rs; r < rows; r += ws.rn) {
+        const long long o = oo[r];
+        if (o < 0) continue;
+        double *p = out + o + (long long)ws.es * P.aout.inc;
+        const double *row = ys + r * ldz;
+        for (int e = ws.es; e < n; e += ws.en, p += ostep) {
+          double v = row[rev ? n - 1 - e : e];
+          if (neg_odd && (e & 1)) v = -v;
+          *p = v;
+        }
       }
-    })
+    }
+    // note: the buffers this tile wrote last (ys in A or zB) are read by slow storers until the next top-of-loop barrier;
+    // the next tile's prefetch only targets the other landing buffer, and A / zB are rewritten after that barrier
   }
-  }  // tile loop
+  cp_async_wait<0>();
 }
 
 /* closed forms for the lengths the reference special-cases (costf1_ n=2,3 fftpack.c:6339-6353; sintf1_ n=2

@@ -93,7 +93,7 @@ void run(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) 
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
-        memset(dyn_smem, 0xA5, smem);  // poison: catches reads of unwritten shared memory
+        memset(dyn_smem, 0xFF, smem);  // poison (all-ones = NaN for doubles): catches reads of unwritten shared memory
         for (int t = 0; t < nthreads; ++t) {
           Fiber &f = fibers[t];
           f.done = false;
