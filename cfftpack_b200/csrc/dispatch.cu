@@ -8,6 +8,7 @@
  * There is no CPU path: a failure to launch is reported to the caller through ier.
  */
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -135,7 +136,8 @@ static bool launch_engine(EngineParams &P) {
 }
 
 /* long power-of-two transforms: both sweeps of the four-step split run in the register tile kernel (pow2.cuh) */
-static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c) {
+static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c,
+                                   double scale) {
   const int n1 = 1 << a1, n2 = 1 << a2;
   const RootPlan *rp = get_root_plan(n);
   if (!rp) return false;
@@ -168,7 +170,7 @@ static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long lo
   P.in = scr;
   P.out = c;
   P.lot = lot * n1;
-  P.scale = dir < 0 ? 1.0 / (double)n : 1.0;
+  P.scale = scale;
   P.fs = nullptr;
   P.fs_count = 0;
   if (!batch_fast) {  // row g = m*n1 + k1: scratch rows are contiguous along j2 -> staged load
@@ -184,9 +186,13 @@ static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long lo
 }
 
 bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void *c) {
+  return run_c2c_scaled(n, lot, inc, jump, dir, c, dir < 0 ? 1.0 / (double)n : 1.0);
+}
+
+bool run_c2c_scaled(int n, long long lot, long long inc, long long jump, int dir, void *c, double scale) {
   if (n <= 1 || lot <= 0) return true;
   const int aligned = (((uintptr_t)c) & 15) == 0;
-  if (pow2_c2c_supported(n, inc, jump, aligned)) return pow2_c2c_launch(n, lot, jump, dir, (cpx *)c);
+  if (pow2_c2c_supported(n, inc, jump, aligned)) return pow2_c2c_launch(n, lot, jump, dir, (cpx *)c, scale);
   EngineParams P;
   memset(&P, 0, sizeof(P));
   P.kind = K_C2C;
@@ -207,7 +213,7 @@ bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void 
     P.ain = P.aout = make_addr(inc, jump, 0, 1LL << 30);
     P.in = c;
     P.out = c;
-    P.scale = dir < 0 ? 1.0 / (double)n : 1.0;
+    P.scale = scale;
     return launch_engine(P);
   }
   /* four-step: x[j1*n2 + j2] -> (FFT over j1) * W_n^{j2 k1} -> scratch[k1*n2 + j2] -> (FFT over j2) -> X[k1 + n1 k2] */
@@ -215,7 +221,7 @@ bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void 
     int a = 0;
     while ((1 << a) < n) ++a;
     const int a1 = a / 2, a2 = a - a1;
-    if (a1 >= pow2_tile_min_log2() && a2 <= pow2_tile_max_log2()) return run_c2c_pow2_four_step(n, a1, a2, lot, inc, jump, dir, (cpx *)c);
+    if (a1 >= pow2_tile_min_log2() && a2 <= pow2_tile_max_log2()) return run_c2c_pow2_four_step(n, a1, a2, lot, inc, jump, dir, (cpx *)c, scale);
   }
   const int n1 = four_step_split(n, engine_max_c2c());
   if (n1 <= 1) {
@@ -271,7 +277,7 @@ bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void 
   }
   P.in = scr;
   P.out = c;
-  P.scale = dir < 0 ? 1.0 / (double)n : 1.0;
+  P.scale = scale;
   P.fs_tw = nullptr;
   P.fs_n = 0;
   P.fs_smem = 0;
@@ -282,6 +288,73 @@ bool run_c2c_2d(int ldim, int l, int m, int dir, void *c) {
   // cfft2f_ order (fftpack.c:2408-2426): lines along the second index first, then along the first
   if (!run_c2c(m, l, ldim, 1, dir, c)) return false;
   return run_c2c(l, m, 1, ldim, dir, c);
+}
+
+/* real-family sequences too long for one CTA: global-memory pipeline around the long complex transform */
+static int long_real_threshold() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CFB200_LONG_REAL_MIN");  // tests lower it to exercise this path with short sequences
+    v = e ? atoi(e) : engine_max_real() + 1;
+  }
+  return v;
+}
+
+static bool run_real_long(int kind, int n, int M, long long lot, long long inc, long long jump, int dir, double *x) {
+  const bool fwd_core = !((kind == K_RFFT || kind == K_COSQ || kind == K_SINQ) && dir > 0);
+  LongRealParams P;
+  memset(&P, 0, sizeof(P));
+  P.kind = kind;
+  P.dir = dir;
+  P.n = n;
+  P.M = M;
+  P.lot = lot;
+  P.ld = (long long)(M > n ? M : n) + 2;
+  P.a = make_addr(inc, jump, 0, 1LL << 30);
+  P.user = x;
+  const long long pairs = (lot + 1) / 2, rows2 = 2 * pairs;
+  char *base = (char *)scratch_get(3, (size_t)rows2 * P.ld * 8 * 2 + (size_t)pairs * P.ld * 16 + (size_t)rows2 * 8 + 64);
+  if (!base) return false;
+  P.xs = (double *)base;
+  P.ys = P.xs + rows2 * P.ld;
+  P.z = (cpx *)(P.ys + rows2 * P.ld);
+  P.dsum = (double *)(P.z + pairs * P.ld);
+  if (kind != K_RFFT) {
+    const TrigPlan *tp = get_trig_plan(kind == K_SINQ ? K_COSQ : kind, n);
+    if (!tp) return false;
+    P.trig = tp->d_trig;
+  }
+  if (lot > 2147483647LL) {
+    set_error("long real path: batch too large");
+    return false;
+  }
+  cudaStream_t st = current_stream();
+  const unsigned gx = (unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+  const unsigned gq = (unsigned)((M / 2 + 256) / 256 < 1024 ? (M / 2 + 256) / 256 : 1024);
+  const unsigned gm = (unsigned)((M + 255) / 256 < 1024 ? (M + 255) / 256 : 1024);
+  const long long YMAX = 65535;
+  int launches = 0;
+  for (P.row0 = 0; P.row0 < lot; P.row0 += YMAX, ++launches)
+    CFB_LAUNCH(long_gather_kernel, dim3(gx, (unsigned)(lot - P.row0 < YMAX ? lot - P.row0 : YMAX)), 256, 0, st, P);
+  CFB_LAUNCH(long_pre_kernel, (unsigned)lot, 32, 0, st, P, fwd_core ? 1 : 0);
+  ++launches;
+  if (!fwd_core)
+    for (P.row0 = 0; P.row0 < pairs; P.row0 += YMAX, ++launches)
+      CFB_LAUNCH(long_build_kernel, dim3(gq, (unsigned)(pairs - P.row0 < YMAX ? pairs - P.row0 : YMAX)), 256, 0, st, P);
+  count_launch(launches);
+  if (!cuda_ok(cudaGetLastError(), "long real pre kernels")) return false;
+  // the real core wants the UNSCALED complex transform (split_pair applies 1/M itself)
+  if (!run_c2c_scaled(M, pairs, 1, P.ld, fwd_core ? -1 : +1, P.z, 1.0)) return false;
+  launches = 0;
+  for (P.row0 = 0; P.row0 < pairs; P.row0 += YMAX, ++launches)
+    CFB_LAUNCH(long_split_kernel, dim3(fwd_core ? gq : gm, (unsigned)(pairs - P.row0 < YMAX ? pairs - P.row0 : YMAX)), 256, 0,
+               st, P, fwd_core ? 1 : 0);
+  CFB_LAUNCH(long_post_kernel, (unsigned)lot, 32, 0, st, P, fwd_core ? 1 : 0);
+  ++launches;
+  for (P.row0 = 0; P.row0 < lot; P.row0 += YMAX, ++launches)
+    CFB_LAUNCH(long_scatter_kernel, dim3(gx, (unsigned)(lot - P.row0 < YMAX ? lot - P.row0 : YMAX)), 256, 0, st, P);
+  count_launch(launches);
+  return cuda_ok(cudaGetLastError(), "long real post kernels");
 }
 
 bool run_real(int kind, int n, long long lot, long long inc, long long jump, int dir, double *x) {
@@ -303,10 +376,7 @@ bool run_real(int kind, int n, long long lot, long long inc, long long jump, int
   if (kind == K_RFFT && pow2_r2c_supported(n, inc, jump, (((uintptr_t)x) & 15) == 0))
     return pow2_r2c_launch(n, lot, jump, dir, x);
   const int M = kind == K_COST ? n - 1 : kind == K_SINT ? n + 1 : n;
-  if (M > engine_max_real()) {
-    set_error("real-family length %d exceeds the single-CTA limit %d", n, engine_max_real());
-    return false;
-  }
+  if (M >= long_real_threshold() || n >= long_real_threshold()) return run_real_long(kind, n, M, lot, inc, jump, dir, x);
   EngineParams P;
   memset(&P, 0, sizeof(P));
   P.kind = kind;

@@ -634,6 +634,87 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
   cp_async_wait<0>();
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Long real-family sequences (longer than one CTA's shared memory): the same pre / pair-packing / split / post
+ * steps as engine_kernel, run from global scratch arrays around the long complex transform of dispatch.cu.
+ * One warp per row; rows are contiguous in the scratch arrays (pitch ld doubles).
+ * ------------------------------------------------------------------------------------------ */
+struct LongRealParams {
+  int kind, dir, n, M;
+  long long lot;      // rows
+  long long row0;     // first row of this launch (gridDim.y is limited to 65535)
+  long long ld;       // pitch of the real scratch rows (doubles) and of the complex rows (cpx)
+  Addr a;             // user layout
+  double *user;       // caller's array
+  double *xs, *ys;    // [lot][ld] real scratch rows
+  cpx *z;             // [(lot+1)/2][ld] complex scratch rows
+  double *dsum;       // [lot]
+  const double *trig;
+};
+
+/* user rows -> xs (sinq: reversed on the forward side) */
+__global__ void __launch_bounds__(256) long_gather_kernel(const LongRealParams P) {
+  const long long row = P.row0 + blockIdx.y;
+  const long long off = batch_off(P.a, row);
+  const bool rev = (P.kind == K_SINQ && P.dir < 0);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < P.n; e += (long long)gridDim.x * blockDim.x)
+    P.xs[row * P.ld + (rev ? P.n - 1 - e : e)] = P.user[off + e * P.a.inc];
+}
+/* ys -> user rows (sinq: sign / reversal on the way out) */
+__global__ void __launch_bounds__(256) long_scatter_kernel(const LongRealParams P) {
+  const long long row = P.row0 + blockIdx.y;
+  const long long off = batch_off(P.a, row);
+  const bool neg_odd = (P.kind == K_SINQ && P.dir < 0), rev = (P.kind == K_SINQ && P.dir > 0);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < P.n; e += (long long)gridDim.x * blockDim.x) {
+    double v = P.ys[row * P.ld + (rev ? P.n - 1 - e : e)];
+    if (neg_odd && (e & 1)) v = -v;
+    P.user[off + e * P.a.inc] = v;
+  }
+}
+/* stage 1 (one warp per row): forward core: xs -> re/im lane of z; backward core: xs -> half-complex row in ys */
+__global__ void __launch_bounds__(32) long_pre_kernel(const LongRealParams P, int fwd_core) {
+  const long long row = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (fwd_core) {
+    double *zc = (double *)(P.z + (row >> 1) * P.ld) + (row & 1);
+    pre_forward_core(P.kind, P.dir, P.n, P.M, P.xs + row * P.ld, zc, P.trig, P.dsum + row, lane);
+    if ((row == P.lot - 1) && !(row & 1))  // odd lot: the missing partner row is zero
+      for (int j = lane; j < P.M; j += 32) zc[2 * j + 1] = 0.0;
+  } else {
+    pre_backward_core(P.kind, P.n, P.xs + row * P.ld, P.ys + row * P.ld, lane);
+    if ((row == P.lot - 1) && !(row & 1))
+      for (int j = lane; j < P.M; j += 32) P.ys[(row + 1) * P.ld + j] = 0.0;
+  }
+}
+/* backward core: half-complex rows (ys) -> spectrum z of the pair */
+__global__ void __launch_bounds__(256) long_build_kernel(const LongRealParams P) {
+  const long long pr = P.row0 + blockIdx.y;
+  const int nfq = P.M / 2 + 1;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nfq; f += gridDim.x * blockDim.x)
+    build_pair(P.z + pr * P.ld, P.ys + (2 * pr) * P.ld, P.ys + (2 * pr + 1) * P.ld, P.M, f);
+}
+/* forward core: z -> half-complex rows (xs);  backward core: z -> real rows (xs) */
+__global__ void __launch_bounds__(256) long_split_kernel(const LongRealParams P, int fwd_core) {
+  const long long pr = P.row0 + blockIdx.y;
+  if (fwd_core) {
+    const int nfq = P.M / 2 + 1;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nfq; f += gridDim.x * blockDim.x)
+      split_pair(P.z + pr * P.ld, P.xs + (2 * pr) * P.ld, P.xs + (2 * pr + 1) * P.ld, P.M, f);
+  } else {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < P.M; e += gridDim.x * blockDim.x) {
+      cpx v = P.z[pr * P.ld + e];
+      P.xs[(2 * pr) * P.ld + e] = v.x;
+      P.xs[(2 * pr + 1) * P.ld + e] = v.y;
+    }
+  }
+}
+/* last stage (one warp per row): xs -> ys */
+__global__ void __launch_bounds__(32) long_post_kernel(const LongRealParams P, int fwd_core) {
+  const long long row = blockIdx.x;
+  post_sequence(P.kind, P.dir, P.n, P.M, P.xs + row * P.ld, P.ys + row * P.ld, P.trig, fwd_core ? P.dsum[row] : 0.0,
+                threadIdx.x);
+}
+
 /* closed forms for the lengths the reference special-cases (costf1_ n=2,3 fftpack.c:6339-6353; sintf1_ n=2
  * :14858-14866; cosqf1_ n=2 :5498-5502; the backward twins) -- one thread per sequence */
 struct TinyParams {

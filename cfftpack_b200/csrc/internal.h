@@ -28,6 +28,7 @@ void scratch_release_all();
 
 /* ---- transform drivers (dispatch.cu).  Pointers are DEVICE pointers; strides in elements. ---- */
 bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void *c);
+bool run_c2c_scaled(int n, long long lot, long long inc, long long jump, int dir, void *c, double scale);
 bool run_real(int kind, int n, long long lot, long long inc, long long jump, int dir, double *x);
 bool run_c2c_2d(int ldim, int l, int m, int dir, void *c);
 

@@ -103,7 +103,7 @@ bool set_smem_once(K kernel, size_t smem, std::once_flag &once, bool &ok) {
 }
 
 template <class C, int MINB, int DIR>
-bool launch_c2c_cfg(long long lot, long long jump, cpx *c) {
+bool launch_c2c_cfg(long long lot, long long jump, cpx *c, double scale) {
   const cpx *tw = pow2_table<C>();
   if (!tw) return false;
   static std::once_flag once;
@@ -111,7 +111,6 @@ bool launch_c2c_cfg(long long lot, long long jump, cpx *c) {
   auto kern = pow2_c2c_kernel<C, MINB, DIR>;
   if (!set_smem_once(kern, C::SMEM, once, ok)) return false;
   const long long grid = (lot + C::TPB - 1) / C::TPB;
-  const double scale = DIR < 0 ? 1.0 / (double)C::N : 1.0;
   CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, C::SMEM, current_stream(), c, lot, jump, tw, scale);
   count_launch();
   return cuda_ok(cudaGetLastError(), "pow2_c2c_kernel launch");
@@ -133,7 +132,7 @@ bool launch_r2c_cfg(long long lot, long long jump, double *r) {
 }
 
 template <class C, int MINB, int DIR>
-bool launch_c2c_stream(long long lot, long long jump, cpx *c) {
+bool launch_c2c_stream(long long lot, long long jump, cpx *c, double scale) {
   const cpx *tw = pow2_stream_table<C>();
   if (!tw) return false;
   static std::once_flag once;
@@ -143,7 +142,6 @@ bool launch_c2c_stream(long long lot, long long jump, cpx *c) {
   const long long ntiles = (lot + C::TPB - 1) / C::TPB;
   const long long cap = (long long)MINB * sm_count();
   const long long grid = ntiles < cap ? ntiles : cap;
-  const double scale = DIR < 0 ? 1.0 / (double)C::N : 1.0;
   CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, StreamSmem<C>::BYTES, current_stream(), c, lot, jump, tw, scale, ntiles);
   count_launch();
   return cuda_ok(cudaGetLastError(), "pow2_c2c_stream_kernel launch");
@@ -182,18 +180,18 @@ struct StreamMinB {
 };
 
 template <int LOG2N, int DIR>
-bool launch_c2c(long long lot, long long jump, cpx *c) {
+bool launch_c2c(long long lot, long long jump, cpx *c, double scale) {
   if (LOG2N == 12) {
     switch (variant()) {
-      case 1: return launch_c2c_cfg<Pow2Cfg<12, 4, 0>, 2, DIR>(lot, jump, c);  // direct loads, table twiddles, 2 CTAs/SM
-      case 2: return launch_c2c_cfg<Pow2Cfg<12, 4, 1>, 2, DIR>(lot, jump, c);  // direct loads, rebuilt twiddles
-      case 3: return launch_c2c_cfg<Pow2Cfg<12, 4, 1>, 3, DIR>(lot, jump, c);  // ... 3 CTAs/SM (spills)
-      case 4: return launch_c2c_cfg<Pow2Cfg<12, 3, 1>, 2, DIR>(lot, jump, c);  // 8 points/thread, 512 threads
-      case 6: return launch_c2c_stream<Pow2Cfg<12, 3, 1>, 2, DIR>(lot, jump, c);  // streaming, 8 points/thread
+      case 1: return launch_c2c_cfg<Pow2Cfg<12, 4, 0>, 2, DIR>(lot, jump, c, scale);  // direct loads, table twiddles, 2 CTAs/SM
+      case 2: return launch_c2c_cfg<Pow2Cfg<12, 4, 1>, 2, DIR>(lot, jump, c, scale);  // direct loads, rebuilt twiddles
+      case 3: return launch_c2c_cfg<Pow2Cfg<12, 4, 1>, 3, DIR>(lot, jump, c, scale);  // ... 3 CTAs/SM (spills)
+      case 4: return launch_c2c_cfg<Pow2Cfg<12, 3, 1>, 2, DIR>(lot, jump, c, scale);  // 8 points/thread, 512 threads
+      case 6: return launch_c2c_stream<Pow2Cfg<12, 3, 1>, 2, DIR>(lot, jump, c, scale);  // streaming, 8 points/thread
       default: break;
     }
   }
-  return launch_c2c_stream<Pow2Cfg<LOG2N>, StreamMinB<LOG2N>::value, DIR>(lot, jump, c);
+  return launch_c2c_stream<Pow2Cfg<LOG2N>, StreamMinB<LOG2N>::value, DIR>(lot, jump, c, scale);
 }
 template <int LOG2N, int DIR>
 bool launch_r2c(long long lot, long long jump, double *r) {
@@ -274,8 +272,8 @@ bool pow2_tile_launch(int log2n, int dir, TileParams &P) {
   return false;
 }
 
-bool pow2_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c) {
-  CFB_POW2_CASES(launch_c2c, lot, jump, c)
+bool pow2_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c, double scale) {
+  CFB_POW2_CASES(launch_c2c, lot, jump, c, scale)
   set_error("pow2_c2c_launch: unsupported length %d", n);
   return false;
 }

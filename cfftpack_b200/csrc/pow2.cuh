@@ -462,7 +462,8 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
           if (vb) xb[N - 1] = v.y * sc;
         }
       }
-      __syncthreads();  // zq is reused by the next tile's first exchange
+      // no barrier needed here: the next tile's first write to this exchange tile comes after its landing-read barrier,
+      // which every thread only reaches once it has finished reading zq above
     } else {
 #pragma unroll
       for (int i = 0; i < P; ++i) {
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_kernel(const TilePara
 /* ---- host side ---- */
 bool pow2_c2c_supported(int n, long long inc, long long jump, int aligned16);
 bool pow2_r2c_supported(int n, long long inc, long long jump, int aligned16);
-bool pow2_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c);
+bool pow2_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c, double scale);
 bool pow2_r2c_launch(int n, long long lot, long long jump, int dir, double *r);
 /* four-step rows: log2 of the row length must be within [pow2_tile_min_log2, pow2_tile_max_log2] */
 int pow2_tile_min_log2();

@@ -302,3 +302,16 @@ def test_reference_own_test_programs_relinked_against_the_cuda_library():
     fb = [float(v) for v in re.findall(r"-?\d+\.\d+", b)]
     assert len(fa) == len(fb) > 100
     assert max(abs(u - v) for u, v in zip(fa, fb)) <= 0.0100001  # printed with two decimals
+
+
+def test_long_real_family_sequences():
+    """sequences longer than one CTA's shared memory (e.g. test/vargamma.c runs rfft up to N = 2^20)"""
+    for fam, n, lot in (("rfft", 32768, 3), ("rfft", 1 << 20, 1), ("cost", 10001, 2), ("sint", 9999, 3), ("cosq", 16384, 2),
+                        ("sinq", 12000, 1), ("rfft", 3 * 5 * 7 * 11 * 13, 2)):
+        x = fl.rand_input(fam, n * lot, n % 1000)
+        for d in "fb":
+            a, ia = PROD.runm(fam, d, lot, n, n, 1, x, work=False)
+            b, ib = ORC.runm(fam, d, lot, n, n, 1, x)
+            assert ia == ib == 0, (fam, d, n, ia, ib, fl.product().cfb200_last_error())
+            worst = max(fl.rel_l2(a[i * n:(i + 1) * n], b[i * n:(i + 1) * n]) for i in range(lot))
+            assert worst <= fl.tol(n), (fam, d, n, worst)

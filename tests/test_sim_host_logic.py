@@ -134,3 +134,29 @@ print('ok')
     env = dict(os.environ, CFB200_PIPE_CHUNK_KB="4")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_long_real_path_forced_on_short_sequences(libs):
+    """real-family sequences longer than one CTA go through global scratch arrays around the long complex transform;
+    CFB200_LONG_REAL_MIN lowers the switch-over so the emulator can cover it"""
+    import subprocess
+    import sys
+    code = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+import fftlibs as fl
+S, O = fl.Lib(fl.sim()), fl.Lib(fl.oracle(), 'orc_')
+for fam in ('rfft', 'cost', 'sint', 'cosq', 'sinq'):
+    for n, lot, jump, inc in ((24, 5, 24, 1), (45, 4, 1, 4), (64, 3, 70, 1), (100, 2, 203, 2)):
+        span = (lot - 1) * jump + (n - 1) * inc + 1
+        x = fl.rand_input(fam, span, 9)
+        for d in 'fb':
+            a, ia = S.runm(fam, d, lot, jump, n, inc, x, lenx=span)
+            b, ib = O.runm(fam, d, lot, jump, n, inc, x, lenx=span)
+            assert ia == ib == 0, (fam, d, n, ia, ib)
+            assert fl.rel_l2(a, b) <= fl.tol(n), (fam, d, n, lot, fl.rel_l2(a, b))
+print('ok')
+""" % os.path.join(fl.ROOT, "tests")
+    env = dict(os.environ, CFB200_LONG_REAL_MIN="20")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-500:] + out.stderr[-2000:]
