@@ -96,7 +96,7 @@ static bool launch_engine(EngineParams &P) {
   P.ldx = 0;
   // bytes per sequence (c2c: three complex rows -- two landing buffers + the ping-pong partner -- and double-buffered
   // row tables) or per pair (real kinds: two complex rows and the row tables)
-  const size_t per = real ? (size_t)P.ldz * 48 + 112 : (size_t)P.ldz * 48 + 64;
+  const size_t per = real ? (size_t)P.ldz * 48 + 256 : (size_t)P.ldz * 48 + 64;
   const size_t fixed = 64 + (size_t)(P.tw_smem + P.fs_smem) * sizeof(cpx);
   const long long units = real ? (P.lot + 1) / 2 : P.lot;
   if (per + fixed > SMEM_MAX) {
@@ -116,7 +116,18 @@ static bool launch_engine(EngineParams &P) {
     while (p2 * 2 <= T) p2 *= 2;
     T = p2;
   }
+  if (real) {  // rows = 2T must be a power of two (thread groups of the pre/post-processing); prefer >= 4 rows per CTA
+    if (T < 2 && (long long)((SMEM_MAX - fixed) / per) >= 2 && units >= 2) T = 2;
+    long long p2 = 1;
+    while (p2 * 2 <= T) p2 *= 2;
+    T = p2;
+  }
   if (T > units) T = units;
+  if (real && T > 1) {  // keep the power of two after clamping to the batch
+    long long p2 = 1;
+    while (p2 * 2 <= T) p2 *= 2;
+    T = p2;
+  }
   P.T = (int)T;
   const long long rows = real ? 2 * T : T;
   // thread tiling of the loader/storer: threads along the contiguous axis first

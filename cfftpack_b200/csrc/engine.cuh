@@ -211,20 +211,46 @@ __device__ __forceinline__ void build_pair(cpx *__restrict__ z, const double *__
   }
 }
 
-/* ---- kind-specific pre-processing of ONE real sequence, done by one warp.
- * x: the loaded sequence (length n, unit stride).  Forward-core kinds write u (length M) into the re or im
+/* ---- kind-specific pre/post-processing of ONE real sequence by a GROUP of gs threads (gs = 32, 64, 128 or 256;
+ * gl = this thread's index in the group).  Groups of more than one warp combine their partial sums / scan carries
+ * through gsc (8 doubles of shared memory per row) and a block barrier, so every thread of the block must make the
+ * call (the engine runs all groups in lockstep; the long-sequence kernels use gs = 32, where no barrier is needed). */
+__device__ __forceinline__ double group_sum(double v, int gl, int gs, double *gsc) {
+  v = warp_sum(v);
+  if (gs > 32) {
+    if ((gl & 31) == 0) gsc[gl >> 5] = v;
+    __syncthreads();
+    v = 0.0;
+    for (int w = 0; w < (gs >> 5); ++w) v += gsc[w];
+  }
+  return v;
+}
+/* exclusive prefix of v over the threads of the group */
+__device__ __forceinline__ double group_excl_scan(double v, int gl, int gs, double *gsc) {
+  const int lane = gl & 31;
+  const double ex = warp_excl_scan(v, lane);
+  if (gs <= 32) return ex;
+  const double tot = __shfl_sync(0xffffffffu, ex + v, 31);
+  if (lane == 0) gsc[gl >> 5] = tot;
+  __syncthreads();
+  double carry = 0.0;
+  for (int w = 0; w < (gl >> 5); ++w) carry += gsc[w];
+  return carry + ex;
+}
+
+/* x: the loaded sequence (length n, unit stride).  Forward-core kinds write u (length M) into the re or im
  * lane of the complex row (zc, stride 2).  Backward-core kinds write the half-complex row h (unit stride). */
 __device__ __forceinline__ void pre_forward_core(int kind, int dir, int n, int M, const double *__restrict__ x,
                                                  double *__restrict__ zc, const double *__restrict__ trig, double *dsum,
-                                                 int lane) {
+                                                 int gl, int gs, double *gsc) {
   if (kind == K_RFFT) {
-    for (int j = lane; j < n; j += 32) zc[2 * j] = x[j];
+    for (int j = gl; j < n; j += gs) zc[2 * j] = x[j];
   } else if (kind == K_COST) {
     // costf1_/costb1_ pre-fold (fftpack.c:6355-6377, :6222-6244); trig[j] = 2 sin(j pi/M), trig[M + j] = 2 cos(j pi/M)
     const int ns2 = n / 2;
     const double e = (dir > 0) ? 2.0 : 1.0;  // backward doubles the end points first
     double part = 0.0;
-    for (int j = 1 + lane; j < ns2; j += 32) {
+    for (int j = 1 + gl; j < ns2; j += gs) {
       int jc = n - 1 - j;
       double t1 = x[j] + x[jc], t2 = x[j] - x[jc];
       part = fma(trig[M + j], t2, part);
@@ -232,8 +258,8 @@ __device__ __forceinline__ void pre_forward_core(int kind, int dir, int n, int M
       zc[2 * j] = t1 - t2;
       if (jc < M) zc[2 * jc] = t1 + t2;
     }
-    part = warp_sum(part);
-    if (lane == 0) {
+    part = group_sum(part, gl, gs, gsc);
+    if (gl == 0) {
       double x0 = e * x[0], xn = e * x[n - 1];
       *dsum = (x0 - xn) + part;
       zc[0] = x0 + xn;
@@ -242,25 +268,25 @@ __device__ __forceinline__ void pre_forward_core(int kind, int dir, int n, int M
   } else if (kind == K_SINT) {
     // sintf1_ pre (fftpack.c:14873-14888); trig[k-1] = 2 sin(k pi/(n+1))
     const int ns2 = n / 2;
-    for (int k = 1 + lane; k <= ns2; k += 32) {
+    for (int k = 1 + gl; k <= ns2; k += gs) {
       int kc = n + 1 - k;
       double t1 = x[k - 1] - x[kc - 1], t2 = trig[k - 1] * (x[k - 1] + x[kc - 1]);
       zc[2 * k] = t1 + t2;
       zc[2 * kc] = t2 - t1;
     }
-    if (lane == 0) {
+    if (gl == 0) {
       zc[0] = 0.0;
       if (n & 1) zc[2 * (ns2 + 1)] = 4.0 * x[ns2];
     }
   } else {  // K_COSQ / K_SINQ forward: cosqf1_ pre (fftpack.c:5693-5717); trig[i] = cos((i+1) pi/(2n))
     const int ns2 = (n + 1) / 2;
-    for (int j = 1 + lane; j < ns2; j += 32) {
+    for (int j = 1 + gl; j < ns2; j += gs) {
       int jc = n - j;
       double a = x[j] + x[jc], b = x[j] - x[jc];
       zc[2 * j] = fma(trig[j - 1], b, trig[jc - 1] * a);
       zc[2 * jc] = fma(trig[j - 1], a, -(trig[jc - 1] * b));
     }
-    if (lane == 0) {
+    if (gl == 0) {
       zc[0] = x[0];
       if (!(n & 1)) zc[2 * ns2] = trig[ns2 - 1] * (x[ns2] + x[ns2]);
     }
@@ -268,30 +294,30 @@ __device__ __forceinline__ void pre_forward_core(int kind, int dir, int n, int M
 }
 
 __device__ __forceinline__ void pre_backward_core(int kind, int n, const double *__restrict__ x, double *__restrict__ h,
-                                                  int lane) {
+                                                  int gl, int gs) {
   if (kind == K_RFFT) {
-    for (int j = lane; j < n; j += 32) h[j] = x[j];
+    for (int j = gl; j < n; j += gs) h[j] = x[j];
   } else {  // cosqb1_ pre (fftpack.c:5604-5616); sinqb1_ first negates the odd entries (fftpack.c:14160-14166)
     const double so = (kind == K_SINQ) ? -1.0 : 1.0;
-    for (int i0 = 2 + 2 * lane; i0 < n; i0 += 64) {
+    for (int i0 = 2 + 2 * gl; i0 < n; i0 += 2 * gs) {
       double a = so * x[i0 - 1], b = x[i0];
       h[i0 - 1] = 0.5 * (a + b);
       h[i0] = 0.5 * (a - b);
     }
-    if (lane == 0) {
+    if (gl == 0) {
       h[0] = 0.5 * x[0];
       if (!(n & 1)) h[n - 1] = 0.5 * so * x[n - 1];
     }
   }
 }
 
-/* ---- kind-specific post-processing of ONE real sequence by one warp: s -> y (both unit stride).
- * s is the half-complex row h (forward core, length M) or the real sequence u (backward core). */
+/* s -> y (both unit stride).  s is the half-complex row h (forward core, length M) or the real sequence u
+ * (backward core). */
 __device__ __forceinline__ void post_sequence(int kind, int dir, int n, int M, const double *__restrict__ s,
                                               double *__restrict__ y, const double *__restrict__ trig, double dsum,
-                                              int lane) {
+                                              int gl, int gs, double *gsc) {
   if (kind == K_RFFT) {
-    for (int j = lane; j < n; j += 32) y[j] = s[j];
+    for (int j = gl; j < n; j += gs) y[j] = s[j];
   } else if (kind == K_COST) {
     // costf1_ post (fftpack.c:6386-6407) / costb1_ post (:6253-6283):
     //   y[0] = c0 h[0]; y[2m] = c1 h'[2m-1]; y[2m-1] = D + sum_{m'<m} c1 h'[2m'];  h' = h with h[M-1] doubled if M even
@@ -299,63 +325,64 @@ __device__ __forceinline__ void post_sequence(int kind, int dir, int n, int M, c
     const double D = dir < 0 ? dsum / (double)M : 0.5 * dsum;
     const int last = (M % 2 == 0) ? M - 1 : -1;
     const int cnt = n / 2;  // odd output indices 2m-1, m = 1..cnt
-    const int chunk = (cnt + 31) / 32;
-    const int m_lo = 1 + lane * chunk, m_hi = min(m_lo + chunk, cnt + 1);
+    const int chunk = (cnt + gs - 1) / gs;
+    const int m_lo = 1 + gl * chunk, m_hi = min(m_lo + chunk, cnt + 1);
     double loc = 0.0;  // sum over my m of c1*h'[2m]
     for (int mm = m_lo; mm < m_hi; ++mm) {
       int i = 2 * mm;
       if (i < M) loc += c1 * (i == last ? 2.0 * s[i] : s[i]);
     }
-    double run = D + warp_excl_scan(loc, lane);
+    double run = D + group_excl_scan(loc, gl, gs, gsc);
     for (int mm = m_lo; mm < m_hi; ++mm) {
       int i = 2 * mm;
       y[i - 1] = run;
       if (i < M) run += c1 * (i == last ? 2.0 * s[i] : s[i]);
       if (i < n) y[i] = c1 * ((i - 1) == last ? 2.0 * s[i - 1] : s[i - 1]);
     }
-    __syncwarp();
-    if (lane == 0) {
-      y[0] = c0 * s[0];
-      if (dir < 0) y[n - 1] *= 0.5;
+    // y[0] and (forward) the halving of y[n-1]: done by the thread that produced y[n-1]
+    if (gl == 0) y[0] = c0 * s[0];
+    if (dir < 0) {
+      const int owner_m = (n - 1 + 1) / 2;  // y[n-1] is written in iteration mm = ceil((n-1)/2) (as y[2mm-1] or y[2mm])
+      if (owner_m >= m_lo && owner_m < m_hi) y[n - 1] *= 0.5;
     }
   } else if (kind == K_SINT) {
     // sintf1_ post (fftpack.c:14898-14919): y[2m] = sc h[0] + sum_{m'<=m} sc h[2m'-1]; y[2m-1] = sc h[2m]
     const double sc = dir < 0 ? 0.5 : 0.25 * (double)M;
     const int cnt = (n - 1) / 2;  // even output indices 2m, m = 1..cnt
-    const int chunk = (cnt + 31) / 32;
-    const int m_lo = 1 + lane * chunk, m_hi = min(m_lo + chunk, cnt + 1);
+    const int chunk = (cnt + gs - 1) / gs;
+    const int m_lo = 1 + gl * chunk, m_hi = min(m_lo + chunk, cnt + 1);
     double loc = 0.0;
     for (int mm = m_lo; mm < m_hi; ++mm) loc += sc * s[2 * mm - 1];
-    double run = sc * s[0] + warp_excl_scan(loc, lane);
+    double run = sc * s[0] + group_excl_scan(loc, gl, gs, gsc);
     for (int mm = m_lo; mm < m_hi; ++mm) {
       run += sc * s[2 * mm - 1];
       y[2 * mm] = run;
       y[2 * mm - 1] = sc * s[2 * mm];
     }
-    if (lane == 0) {
+    if (gl == 0) {
       y[0] = sc * s[0];
       if (!(n & 1)) y[n - 1] = sc * s[n];
     }
   } else if (dir < 0) {  // cosqf1_ post (fftpack.c:5731-5738)
-    for (int i0 = 2 + 2 * lane; i0 < n; i0 += 64) {
+    for (int i0 = 2 + 2 * gl; i0 < n; i0 += 2 * gs) {
       double a = s[i0 - 1], b = s[i0];
       y[i0 - 1] = 0.5 * (a + b);
       y[i0] = 0.5 * (a - b);
     }
-    if (lane == 0) {
+    if (gl == 0) {
       y[0] = s[0];
       if (!(n & 1)) y[n - 1] = s[n - 1];
     }
   } else {  // cosqb1_ post (fftpack.c:5625-5652)
     const int ns2 = (n + 1) / 2;
-    for (int j = 1 + lane; j < ns2; j += 32) {
+    for (int j = 1 + gl; j < ns2; j += gs) {
       int jc = n - j;
       double p = fma(trig[j - 1], s[jc], trig[jc - 1] * s[j]);
       double q = fma(trig[j - 1], s[j], -(trig[jc - 1] * s[jc]));
       y[j] = p + q;
       y[jc] = p - q;
     }
-    if (lane == 0) {
+    if (gl == 0) {
       y[0] = s[0] + s[0];
       if (!(n & 1)) y[ns2] = trig[ns2 - 1] * (s[ns2] + s[ns2]);
     }
@@ -536,7 +563,8 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
   long long *off_in = (long long *)(A + T * ldz);  // [3][rows]
   long long *off_out = off_in + 3 * rows;           // [3][rows]
   double *dsum = (double *)(off_out + 3 * rows);    // [rows]
-  cpx *tws = (cpx *)(((uintptr_t)(dsum + rows) + 15) & ~(uintptr_t)15);
+  double *gsc = dsum + rows;                        // [rows][8] partial sums / scan carries of multi-warp groups
+  cpx *tws = (cpx *)(((uintptr_t)(gsc + 8 * rows) + 15) & ~(uintptr_t)15);
   const cpx *tw = P.tw;
   if (P.tw_smem > 0) {
     for (int i = tid; i < P.tw_smem; i += nthr) tws[i] = __ldg(P.tw + i);
@@ -553,7 +581,9 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
   };
   const int kind = P.kind, dir = P.dir;
   const bool fwd_core = !((kind == K_RFFT || kind == K_COSQ || kind == K_SINQ) && dir > 0);
-  const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+  // pre/post-processing: the block splits into `groups` groups of gs threads, one row each at a time (rows and the
+  // block size are powers of two, so every group makes the same number of trips -- required by the barriers inside)
+  const int gs = (nthr / rows) < 32 ? 32 : (nthr / rows), groups = nthr / gs, gid = tid / gs, gl = tid % gs;
   const TileWalk ws = tile_walk(tid, nthr, P.tx_out_log2, P.aout.lanes_t);
   const long long ostep = (long long)ws.en * P.aout.inc;
   long long tile = blockIdx.x;
@@ -573,8 +603,9 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
     cpx *cur, *oth;
     double *ys;
     if (fwd_core) {
-      for (int r = warp; r < rows; r += nwarp)
-        pre_forward_core(kind, dir, n, M, rowsB + r * ldz, (double *)(A + (r >> 1) * ldz) + (r & 1), P.trig, dsum + r, lane);
+      for (int r = gid; r < rows; r += groups)
+        pre_forward_core(kind, dir, n, M, rowsB + r * ldz, (double *)(A + (r >> 1) * ldz) + (r & 1), P.trig, dsum + r, gl, gs,
+                         gsc + 8 * r);
       __syncthreads();
       cur = A;
       oth = zB;
@@ -587,9 +618,10 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
       __syncthreads();
       /* post: half-complex rows (oth) -> result rows (cur, no longer needed) */
       ys = (double *)cur;
-      for (int r = warp; r < rows; r += nwarp) post_sequence(kind, dir, n, M, hs + r * ldz, ys + r * ldz, P.trig, dsum[r], lane);
+      for (int r = gid; r < rows; r += groups)
+        post_sequence(kind, dir, n, M, hs + r * ldz, ys + r * ldz, P.trig, dsum[r], gl, gs, gsc + 8 * r);
     } else {
-      for (int r = warp; r < rows; r += nwarp) pre_backward_core(kind, n, rowsB + r * ldz, rowsA + r * ldz, lane);
+      for (int r = gid; r < rows; r += groups) pre_backward_core(kind, n, rowsB + r * ldz, rowsA + r * ldz, gl, gs);
       __syncthreads();
       const int nfq = M / 2 + 1;
       for (int t = 0; t < T; ++t)
@@ -608,7 +640,8 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
         }
       __syncthreads();
       ys = (double *)cur;
-      for (int r = warp; r < rows; r += nwarp) post_sequence(kind, dir, n, M, us + r * ldz, ys + r * ldz, P.trig, 0.0, lane);
+      for (int r = gid; r < rows; r += groups)
+        post_sequence(kind, dir, n, M, us + r * ldz, ys + r * ldz, P.trig, 0.0, gl, gs, gsc + 8 * r);
     }
     __syncthreads();
     /* store: result rows -> global.  sinq: forward negates the odd entries, backward reverses (fftpack.c:14257-14266) */
@@ -677,11 +710,11 @@ __global__ void __launch_bounds__(32) long_pre_kernel(const LongRealParams P, in
   const int lane = threadIdx.x;
   if (fwd_core) {
     double *zc = (double *)(P.z + (row >> 1) * P.ld) + (row & 1);
-    pre_forward_core(P.kind, P.dir, P.n, P.M, P.xs + row * P.ld, zc, P.trig, P.dsum + row, lane);
+    pre_forward_core(P.kind, P.dir, P.n, P.M, P.xs + row * P.ld, zc, P.trig, P.dsum + row, lane, 32, nullptr);
     if ((row == P.lot - 1) && !(row & 1))  // odd lot: the missing partner row is zero
       for (int j = lane; j < P.M; j += 32) zc[2 * j + 1] = 0.0;
   } else {
-    pre_backward_core(P.kind, P.n, P.xs + row * P.ld, P.ys + row * P.ld, lane);
+    pre_backward_core(P.kind, P.n, P.xs + row * P.ld, P.ys + row * P.ld, lane, 32);
     if ((row == P.lot - 1) && !(row & 1))
       for (int j = lane; j < P.M; j += 32) P.ys[(row + 1) * P.ld + j] = 0.0;
   }
@@ -712,7 +745,7 @@ __global__ void __launch_bounds__(256) long_split_kernel(const LongRealParams P,
 __global__ void __launch_bounds__(32) long_post_kernel(const LongRealParams P, int fwd_core) {
   const long long row = blockIdx.x;
   post_sequence(P.kind, P.dir, P.n, P.M, P.xs + row * P.ld, P.ys + row * P.ld, P.trig, fwd_core ? P.dsum[row] : 0.0,
-                threadIdx.x);
+                threadIdx.x, 32, nullptr);
 }
 
 /* closed forms for the lengths the reference special-cases (costf1_ n=2,3 fftpack.c:6339-6353; sintf1_ n=2
