@@ -315,3 +315,43 @@ def test_long_real_family_sequences():
             assert ia == ib == 0, (fam, d, n, ia, ib, fl.product().cfb200_last_error())
             worst = max(fl.rel_l2(a[i * n:(i + 1) * n], b[i * n:(i + 1) * n]) for i in range(lot))
             assert worst <= fl.tol(n), (fam, d, n, worst)
+
+
+def test_concurrent_host_threads_share_wsave():
+    """the reference is re-entrant (SURVEY 8(b) threading): concurrent calls with disjoint data and a shared wsave"""
+    import threading
+    fam, n, lot = "cfft", 1000, 64
+    ws, ier = PROD.init(fam, n, multi=True)
+    xs = [fl.rand_input(fam, n * lot, 100 + i) for i in range(6)]
+    want = [ORC.runm(fam, "f", lot, n, n, 1, x)[0] for x in xs]
+    got = [None] * len(xs)
+
+    def work(i):
+        for _ in range(5):
+            got[i], ier = PROD.runm(fam, "f", lot, n, n, 1, xs[i], ws=ws, work=False)
+            assert ier == 0
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(xs))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(len(xs)):
+        assert fl.rel_l2(got[i], want[i]) <= fl.tol(n), i
+
+
+def test_user_stream_ordering():
+    """device-pointer calls are asynchronous on the stream given to cfb200_set_stream"""
+    torch = _torch()
+    import cfftpack_b200 as cb
+    n, lot = 4096, 4096
+    s = torch.cuda.Stream()
+    plan = cb.Plan("cfft", n)
+    with torch.cuda.stream(s):
+        cb.set_stream(s.cuda_stream)
+        x = torch.rand(lot * n, 2, device="cuda", dtype=torch.float64) - 0.5
+        x0 = x.clone()
+        assert plan.multi("f", x.data_ptr(), lot, n, 1, lot * n) == 0
+        assert plan.multi("b", x.data_ptr(), lot, n, 1, lot * n) == 0
+        err = (x - x0).norm() / x0.norm()  # enqueued on the same stream: sees both transforms
+    s.synchronize()
+    cb.set_stream(0)
+    assert float(err) <= fl.tol(n)
