@@ -406,6 +406,18 @@ CFB_DEF_REAL(sint, K_SINT)
 CFB_DEF_REAL(cosq, K_COSQ)
 CFB_DEF_REAL(sinq, K_SINQ)
 
+int cfb200_cfft2_sharded_phase(int phase, int direction, int l, int m, int rank, int nranks, void *local_src,
+                               void *const *peer_dst, int *ier) {
+  *ier = 0;
+  if (phase < 1 || phase > 2 || nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks || l < 1 || m < 1) {
+    *ier = 1;
+    return 0;
+  }
+  if (!device_ready() || !run_c2c_2d_sharded_phase(phase, direction < 0 ? -1 : +1, l, m, rank, nranks, local_src, peer_dst))
+    *ier = -1;
+  return 0;
+}
+
 int cfb200_set_stream(void *s) {
   set_current_stream((cudaStream_t)s);
   return 0;

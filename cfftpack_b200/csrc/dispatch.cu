@@ -147,8 +147,17 @@ static bool launch_engine(EngineParams &P) {
 }
 
 /* long power-of-two transforms: both sweeps of the four-step split run in the register tile kernel (pow2.cuh) */
+/* destination of the second sweep when the output is spread over peer GPUs (sharded 2-D transform) */
+struct PeerOut {
+  int npeers = 0;
+  cpx *const *peers = nullptr;
+  long long chunk = 0;   // elements of the transform axis owned by each peer
+  long long base = 0;    // offset added on every peer
+  long long row_inc = 0, row_jump = 0, elem_inc = 0;  // layout on the peers: index = base + m*row_jump + (e % chunk)*elem_inc
+};
+
 static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c,
-                                   double scale) {
+                                   double scale, const PeerOut *po = nullptr) {
   const int n1 = 1 << a1, n2 = 1 << a2;
   const RootPlan *rp = get_root_plan(n);
   if (!rp) return false;
@@ -192,6 +201,21 @@ static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long lo
     P.ain = make_addr(lot, 1, (long long)n2 * lot, lot);
     P.aout = make_addr((long long)n1 * inc, jump, inc, lot);
     P.in_staged = 0;
+  }
+  if (po && po->npeers > 0) {
+    // output element k = k1 + n1*e of sequence m lives on peer k / chunk at base + m*row_jump + (k % chunk)*elem_inc
+    if (po->chunk % n1 || po->npeers > 16) {
+      set_error("sharded transform: slab of %lld elements is not a multiple of %d", po->chunk, n1);
+      return false;
+    }
+    int sh = 0;
+    while ((1LL << sh) < po->chunk / n1) ++sh;
+    P.npeers = po->npeers;
+    P.peer_shift = sh;
+    P.out_base = po->base;
+    for (int i = 0; i < po->npeers; ++i) P.peers[i] = po->peers[i];
+    if (!batch_fast) P.aout = make_addr((long long)n1 * po->elem_inc, po->elem_inc, po->row_jump, n1);
+    else P.aout = make_addr((long long)n1 * po->elem_inc, po->row_jump, po->elem_inc, lot);
   }
   return pow2_tile_launch(a2, dir, P);
 }
@@ -293,6 +317,44 @@ bool run_c2c_scaled(int n, long long lot, long long inc, long long jump, int dir
   P.fs_n = 0;
   P.fs_smem = 0;
   return launch_engine(P);
+}
+
+/* One phase of the sharded 2-D transform, fused with its transpose: the local length-n transforms of
+ * this rank's slab are computed and their results stored directly into the slabs of the GPUs that own them.
+ *   phase 1: src = my column slab C[m_loc][l] (sequences contiguous);  result element (i, j) -> rank i / l_loc,
+ *            D_r[j * l_loc + i % l_loc]                     (D = row slab, column-major (l_loc, m))
+ *   phase 2: src = my row slab D[m][l_loc] (sequences along m, stride l_loc); result element (i, j) -> rank j / m_loc,
+ *            C_r[(j % m_loc) * l + i]
+ * The forward direction scales each phase by 1/n like cfftmf_ (total 1/(l m), as cfft2f_). */
+bool run_c2c_2d_sharded_phase(int phase, int dir, int l, int m, int rank, int nranks, void *src, void *const *peers) {
+  const int l_loc = l / nranks, m_loc = m / nranks;
+  const int n = phase == 1 ? l : m;
+  if ((n & (n - 1)) != 0 || l % nranks || m % nranks) {
+    set_error("sharded 2-D transform needs power-of-two l, m divisible by the number of ranks");
+    return false;
+  }
+  int a = 0;
+  while ((1 << a) < n) ++a;
+  const int a1 = a / 2, a2 = a - a1;
+  if (a1 < pow2_tile_min_log2() || a2 > pow2_tile_max_log2()) {
+    set_error("sharded 2-D transform: length %d outside the fused path (2^12 .. 2^20)", n);
+    return false;
+  }
+  PeerOut po;
+  po.npeers = nranks;
+  po.peers = (cpx *const *)peers;
+  if (phase == 1) {
+    po.chunk = l_loc;
+    po.base = (long long)rank * m_loc * l_loc;
+    po.row_jump = l_loc;  // sequence j_loc -> column (rank*m_loc + j_loc) of D
+    po.elem_inc = 1;
+    return run_c2c_pow2_four_step(l, a1, a2, m_loc, 1, l, dir, (cpx *)src, dir < 0 ? 1.0 / (double)l : 1.0, &po);
+  }
+  po.chunk = m_loc;
+  po.base = (long long)rank * l_loc;
+  po.row_jump = 1;    // sequence i_loc -> row rank*l_loc + i_loc of C
+  po.elem_inc = l;    // output index j_loc -> column j_loc of C (pitch l)
+  return run_c2c_pow2_four_step(m, a1, a2, l_loc, l_loc, 1, dir, (cpx *)src, dir < 0 ? 1.0 / (double)m : 1.0, &po);
 }
 
 bool run_c2c_2d(int ldim, int l, int m, int dir, void *c) {

@@ -493,6 +493,12 @@ struct TileParams {
   const cpx *fs;  // split twiddle tables of the long length (nullptr: none)
   int fs_shift, fs_from_hi, fs_count;
   int in_staged;  // 1: rows are contiguous along the element axis on the input side
+  // sharded 2-D transform: the transform axis of the OUTPUT is split over npeers GPUs in chunks of 2^peer_shift
+  // elements; element e goes to peers[e >> peer_shift] (a peer-mapped pointer, NVLink store) at local index
+  // e & (2^peer_shift - 1).  npeers = 0: everything goes to `out`.
+  cpx *peers[16];
+  int npeers, peer_shift;
+  long long out_base;
 };
 
 template <class C>
@@ -556,7 +562,17 @@ __global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_kernel(const TilePara
     __syncthreads();
   }
   pow2_core<C, DIR>(a, sm, t, P.tw);
-  if (live) {
+  if (live && P.npeers > 0) {
+    // fused transpose: each element is stored straight into the memory of the GPU that owns its slab
+    const double scale = P.scale;
+    const int emask = (1 << P.peer_shift) - 1;
+#pragma unroll
+    for (int i = 0; i < PP; ++i) {
+      const int e = t + NT * i;
+      cpx *dst = P.peers[e >> P.peer_shift] + P.out_base + oout + (long long)(e & emask) * P.aout.inc;
+      *dst = make_double2(a[i].x * scale, a[i].y * scale);
+    }
+  } else if (live) {
     cpx *y = P.out + oout + (long long)t * P.aout.inc;
     const long long st = (long long)NT * P.aout.inc;
     const double scale = P.scale;

@@ -90,3 +90,62 @@ class Cfft2Sharded:
 
     def backward(self, c_loc):
         return self.transform(c_loc, "b")
+
+
+class Cfft2ShardedP2P:
+    """Same transform as Cfft2Sharded, with the transposes FUSED into the FFT kernels: the last pass of each dimension
+    stores every result straight into the slab of the GPU that owns it (P2P stores over NVLink/NVSwitch on
+    peer-mapped symmetric memory), so there is no pack kernel and no NCCL all-to-all.  One stream-ordered barrier per
+    phase.  Needs power-of-two l, m in 2^12..2^20 and all ranks on one node.
+
+    `slab` is this rank's column slab C[m_loc][l] (complex128) living in symmetric memory: fill it, call
+    forward()/backward(), read the result from it."""
+
+    def __init__(self, l, m, group=None, lib=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        if lib is None:
+            from . import lib as product_lib
+            lib = product_lib
+        self.lib = lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        G = self.world
+        if l % G or m % G:
+            raise ValueError(f"l={l} and m={m} must be multiples of the number of ranks {G}")
+        self.l, self.m, self.l_loc, self.m_loc = l, m, l // G, m // G
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # complex128 slabs as float64 pairs (symmetric memory allocations are dtype-agnostic byte buffers)
+        self._c = symm_mem.empty(self.m_loc * l * 2, dtype=torch.float64, device=dev)
+        self._d = symm_mem.empty(m * self.l_loc * 2, dtype=torch.float64, device=dev)
+        self._hc = symm_mem.rendezvous(self._c, self.group)
+        self._hd = symm_mem.rendezvous(self._d, self.group)
+        self.slab = torch.view_as_complex(self._c.view(self.m_loc, l, 2))
+        self._c_ptrs = (ctypes.c_void_p * G)(*[int(p) for p in self._hc.buffer_ptrs])
+        self._d_ptrs = (ctypes.c_void_p * G)(*[int(p) for p in self._hd.buffer_ptrs])
+
+    def _phase(self, phase, direction, src, peers):
+        ier = _I(-1)
+        self.lib.cfb200_cfft2_sharded_phase(_I(phase), _I(-1 if direction == "f" else 1), _I(self.l), _I(self.m),
+                                            _I(self.rank), _I(self.world), ctypes.c_void_p(src), peers, ctypes.byref(ier))
+        if ier.value:
+            from . import last_error
+            raise RuntimeError(f"cfb200_cfft2_sharded_phase({phase}): ier={ier.value}: {last_error()}")
+
+    def transform(self, direction):
+        import torch
+        self.lib.cfb200_set_stream(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._hd.barrier(channel=0)   # every rank is done reading its row slab from the previous call
+        self._phase(1, direction, self._c.data_ptr(), self._d_ptrs)
+        self._hd.barrier(channel=0)   # all row slabs are complete
+        self._phase(2, direction, self._d.data_ptr(), self._c_ptrs)
+        self._hc.barrier(channel=0)   # all column slabs are complete
+        return self.slab
+
+    def forward(self):
+        return self.transform("f")
+
+    def backward(self):
+        return self.transform("b")

@@ -72,6 +72,16 @@ CFB200_DECL_TRIG(cosq)
 CFB200_DECL_TRIG(sinq)
 
 /* ---- extensions (no counterpart in the reference) ---- */
+/* Sharded cfft2f_/cfft2b_: matrix c(l, m) column-major distributed over `nranks` GPUs of one node.
+ * phase 1: local_src = this rank's column slab C[m/nranks][l]; every rank's row slab D[m][l/nranks] is given by
+ *          peer_dst[r] (peer-mapped device pointers).  The length-l transforms of the slab are computed and each
+ *          result is stored straight into the owning GPU's D (NVLink P2P stores fused into the last pass).
+ * phase 2: local_src = this rank's D; peer_dst[r] = every rank's C; length-m transforms, results back into C.
+ * The caller synchronises the ranks between the phases (all writes into D/C must have landed).
+ * direction < 0: forward (each phase scaled by 1/n like cfftmf_), > 0: backward.  l, m powers of two in 2^12..2^20,
+ * divisible by nranks.  ier: 0 ok, 1 bad argument, -1 CUDA failure / unsupported size (cfb200_last_error()). */
+int cfb200_cfft2_sharded_phase(int phase, int direction, int l, int m, int rank, int nranks, void *local_src,
+                               void *const *peer_dst, int *ier);
 /* CUDA stream (cudaStream_t) used by THIS host thread for device-pointer calls; NULL = default stream */
 int cfb200_set_stream(void *cuda_stream);
 /* block until the calling thread's stream is idle; returns 0 or -1 */
