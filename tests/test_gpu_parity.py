@@ -355,3 +355,37 @@ def test_user_stream_ordering():
     s.synchronize()
     cb.set_stream(0)
     assert float(err) <= fl.tol(n)
+
+
+def test_repeatability_and_sampled_parity_at_full_occupancy():
+    """every kernel family with enough tiles that each persistent CTA walks many of them: repeated runs must agree
+    bit for bit (a race between pipeline stages shows up as run-to-run differences) and sampled rows match the oracle"""
+    torch = _torch()
+    import cfftpack_b200 as cb
+    cases = [("cfft", 4096, 8192, 4096, 1), ("rfft", 4096, 8191, 4096, 1), ("cfft", 1000, 30000, 1000, 1),
+             ("cfft", 360, 40000, 1, 40000), ("cosq", 1000, 8192, 1000, 1), ("cost", 1001, 4097, 1001, 1),
+             ("sint", 1000, 4096, 1, 4096), ("cfft", 16384, 700, 16384, 1), ("cfft", 16384, 512, 1, 512),
+             ("rfft", 1000, 30001, 1000, 1)]
+    for fam, n, lot, jump, inc in cases:
+        esz = 2 if fam == "cfft" else 1
+        span = (lot - 1) * jump + (n - 1) * inc + 1
+        g = torch.Generator(device="cuda").manual_seed(n + lot)
+        x0 = torch.rand(span * esz, generator=g, device="cuda", dtype=torch.float64) - 0.5
+        plan = cb.Plan(fam, n)
+        outs = []
+        for rep in range(4):
+            x = x0.clone()
+            assert plan.multi("f", x.data_ptr(), lot, jump, inc, span) == 0, cb.last_error()
+            cb.synchronize()
+            outs.append(x)
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0]), (fam, n, lot, "run-to-run difference")
+        host_in = x0.cpu().numpy()
+        host_out = outs[0].cpu().numpy()
+        if fam == "cfft":
+            host_in = host_in.view(np.complex128)
+            host_out = host_out.view(np.complex128)
+        for mrow in (0, 1, lot // 2, lot - 2, lot - 1):
+            idx = mrow * jump + inc * np.arange(n)
+            want, ier = ORC.run1(fam, "f", n, host_in[idx])
+            assert fl.rel_l2(host_out[idx], want) <= fl.tol(n), (fam, n, lot, mrow)
