@@ -172,5 +172,102 @@ struct Dft<16, DIR> {
   static __device__ __forceinline__ void run(cpx (&a)[16]) { dft16<DIR>(a); }
 };
 
+/* odd prime R (7, 11, 13) in registers: symmetric sums, (R-1)^2/2 complex-by-real products.
+ * rt[j] = exp(-2 pi i j / R) (forward convention), j < R, typically in shared memory */
+template <int R, int DIR>
+__device__ __forceinline__ void dft_odd(cpx (&a)[R], const cpx *__restrict__ rt) {
+  constexpr int H = (R - 1) / 2;
+  double c[H + 1], sn[H + 1];
+#pragma unroll
+  for (int j = 1; j <= H; ++j) {
+    const cpx w = rt[j];
+    c[j] = w.x;
+    sn[j] = -w.y;  // sin(2 pi j / R)
+  }
+  cpx p[H + 1], m[H + 1];
+  cpx x0 = a[0];
+#pragma unroll
+  for (int j = 1; j <= H; ++j) {
+    p[j] = cadd(a[j], a[R - j]);
+    m[j] = csub(a[j], a[R - j]);
+    x0 = cadd(x0, p[j]);
+  }
+  const cpx a0 = a[0];
+#pragma unroll
+  for (int k = 1; k <= H; ++k) {
+    double ar = a0.x, ai = a0.y, br = 0.0, bi = 0.0;
+#pragma unroll
+    for (int j = 1; j <= H; ++j) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int idx = (j * k) % R;                 // compile-time after unrolling
+      const int h = idx <= H ? idx : R - idx;      // cos is even, sin is odd about R/2
+      const double cc = c[h], ss = idx <= H ? sn[h] : -sn[h];
+      ar = fma(cc, p[j].x, ar);
+      ai = fma(cc, p[j].y, ai);
+      br = fma(ss, m[j].x, br);
+      bi = fma(ss, m[j].y, bi);
+    }
+    // X_k = A + DIR*i*B, X_{R-k} = A - DIR*i*B with B = (br, bi)
+    if (DIR < 0) {
+      a[k] = make_double2(ar + bi, ai - br);
+      a[R - k] = make_double2(ar - bi, ai + br);
+    } else {
+      a[k] = make_double2(ar - bi, ai + br);
+      a[R - k] = make_double2(ar + bi, ai - br);
+    }
+  }
+  a[0] = x0;
+}
+
+/* composite radix R = A*B in registers (6 = 2*3, 9 = 3*3, 10 = 2*5): B-point... two levels with the R-th roots from
+ * rt[j] = exp(-2 pi i j / R).  Natural order in and out. */
+template <int A, int B, int DIR>
+__device__ __forceinline__ void dft_comp(cpx (&a)[A * B], const cpx *__restrict__ rt) {
+  constexpr int R = A * B;
+  // X[k1 + A*k2] = sum_{i<B} w_R^{i k1} w_B^{i k2} [ sum_{j<A} x[i + B j] w_A^{j k1} ],  k1 < A, k2 < B
+  cpx t[R];
+#pragma unroll
+  for (int i = 0; i < B; ++i) {
+    cpx u[A];
+#pragma unroll
+    for (int j = 0; j < A; ++j) u[j] = a[i + B * j];
+    Dft<A, DIR>::run(u);
+#pragma unroll
+    for (int k1 = 0; k1 < A; ++k1) t[k1 * B + i] = (i * k1 == 0) ? u[k1] : ctw<DIR>(u[k1], rt[(i * k1) % R]);
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < A; ++k1) {
+    cpx v[B];
+#pragma unroll
+    for (int i = 0; i < B; ++i) v[i] = t[k1 * B + i];
+    Dft<B, DIR>::run(v);
+#pragma unroll
+    for (int k2 = 0; k2 < B; ++k2) a[k1 + A * k2] = v[k2];
+  }
+}
+
+/* uniform entry point for the engine: radices that need the table of R-th roots take it from rt */
+template <int R, int DIR>
+struct DftRt {
+  static __device__ __forceinline__ void run(cpx (&a)[R], const cpx *) { Dft<R, DIR>::run(a); }
+};
+#define CFB_DFT_ODD(R)                                                                                  \
+  template <int DIR>                                                                                     \
+  struct DftRt<R, DIR> {                                                                                 \
+    static __device__ __forceinline__ void run(cpx (&a)[R], const cpx *rt) { dft_odd<R, DIR>(a, rt); }   \
+  };
+CFB_DFT_ODD(7)
+CFB_DFT_ODD(11)
+CFB_DFT_ODD(13)
+#define CFB_DFT_COMP(A, B)                                                                                        \
+  template <int DIR>                                                                                               \
+  struct DftRt<(A) * (B), DIR> {                                                                                   \
+    static __device__ __forceinline__ void run(cpx (&a)[(A) * (B)], const cpx *rt) { dft_comp<A, B, DIR>(a, rt); } \
+  };
+CFB_DFT_COMP(2, 3)
+CFB_DFT_COMP(3, 3)
+CFB_DFT_COMP(2, 5)
+
 }  // namespace cfb
 #endif

@@ -48,7 +48,7 @@ __device__ __forceinline__ void pass_fixed(const cpx *__restrict__ src, cpx *__r
     const cpx *sp = src + t * ldz;
 #pragma unroll
     for (int j = 0; j < R; ++j) a[j] = sp[padx(b + j * nb, ps)];
-    Dft<R, DIR>::run(a);
+    DftRt<R, DIR>::run(a, tw + pd.rtoff);
     cpx *dp = dst + t * ldz;
     const int o0 = q + s * R * p;
     dp[padx(o0, ps)] = a[0];
@@ -129,7 +129,13 @@ __device__ __forceinline__ void run_passes(cpx *&cur, cpx *&oth, const EnginePar
       case 3: pass_fixed<3, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
       case 4: pass_fixed<4, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
       case 5: pass_fixed<5, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 6: pass_fixed<6, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 7: pass_fixed<7, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
       case 8: pass_fixed<8, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 9: pass_fixed<9, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 10: pass_fixed<10, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 11: pass_fixed<11, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 13: pass_fixed<13, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
       default: pass_generic<DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
     }
     __syncthreads();

@@ -46,13 +46,22 @@ void unit_root(long long num, long long den, double *re, double *im) {
 }
 
 int engine_factor(int M, int *radix) {
-  int nf = 0, a = 0;
-  while (M % 2 == 0) {
-    M /= 2;
-    ++a;
-  }
-  // power of two: 8s first (the first pass's scattered stores are conflict-free with one pad slot per 8 elements),
-  // then the remainder as 4s / one 2 (the engine keeps <= 8 points per thread)
+  // prime-power counts of the small primes
+  int c2 = 0, c3 = 0, c5 = 0;
+  while (M % 2 == 0) { M /= 2; ++c2; }
+  while (M % 3 == 0) { M /= 3; ++c3; }
+  while (M % 5 == 0) { M /= 5; ++c5; }
+  int nf = 0;
+  // the power of two that is NOT paired into radix 10 / 6 below goes first as 8s (the first pass's scattered stores
+  // are conflict-free with one pad slot per 8 elements), then 4s / one 2 -- the engine keeps <= 13 points per thread
+  int pair10 = c2 < c5 ? c2 : c5;          // (2,5) -> 10: one pass instead of two
+  int a = c2 - pair10;
+  int f5 = c5 - pair10;
+  int pair9 = c3 / 2;                      // (3,3) -> 9
+  int f3 = c3 - 2 * pair9;
+  int pair6 = (a > 0 && f3 > 0 && a % 3 == 1) ? 1 : 0;  // a lone 2 joins a lone 3
+  a -= pair6;
+  f3 -= pair6;
   int tail[2], ntail = 0;
   switch (a % 3) {
     case 1:
@@ -73,14 +82,11 @@ int engine_factor(int M, int *radix) {
     a -= 3;
   }
   for (int i = 0; i < ntail; ++i) radix[nf++] = tail[i];
-  while (M % 5 == 0) {
-    radix[nf++] = 5;
-    M /= 5;
-  }
-  while (M % 3 == 0) {
-    radix[nf++] = 3;
-    M /= 3;
-  }
+  for (int i = 0; i < pair10; ++i) radix[nf++] = 10;
+  for (int i = 0; i < pair9; ++i) radix[nf++] = 9;
+  for (int i = 0; i < pair6; ++i) radix[nf++] = 6;
+  for (int i = 0; i < f5; ++i) radix[nf++] = 5;
+  for (int i = 0; i < f3; ++i) radix[nf++] = 3;
   for (int p = 7; (long long)p * p <= M; p += 2)
     while (M % p == 0) {
       radix[nf++] = p;
