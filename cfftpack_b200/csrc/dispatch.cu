@@ -29,14 +29,11 @@ static bool engine_attr_once() {
   static std::once_flag once;
   static bool ok = true;
   std::call_once(once, [] {
-    ok = cuda_ok(cudaFuncSetAttribute(engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
-                 "cudaFuncSetAttribute(engine_kernel)") &&
-         cuda_ok(cudaFuncSetAttribute(engine_c2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
+    ok = cuda_ok(cudaFuncSetAttribute(engine_c2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
                  "cudaFuncSetAttribute(engine_c2c_kernel)") &&
          cuda_ok(cudaFuncSetAttribute(engine_c2c_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
                  "cudaFuncSetAttribute(engine_c2c_kernel, carveout)") &&
-         cuda_ok(cudaFuncSetAttribute(engine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
-                 "cudaFuncSetAttribute(engine_kernel, carveout)");
+         true;
   });
   return ok;
 }
@@ -70,6 +67,38 @@ static int four_step_split(int n, int limit) {
       best = d;  // largest d <= sqrt(n); n/d shrinks as d grows
     }
   return best;  // n1 = best (<= n2 = n / best)
+}
+
+/* the real-family kernel is instantiated per (family, direction): the family-specific code folds at compile time */
+template <int KIND, int DIR>
+static bool launch_real_kernel(unsigned grid, size_t smem, const EngineParams &P) {
+  static std::once_flag once;
+  static bool ok = true;
+  auto kern = engine_kernel<KIND, DIR>;
+  std::call_once(once, [&] {
+    ok = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
+                 "cudaFuncSetAttribute(engine_kernel)") &&
+         cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
+                 "cudaFuncSetAttribute(engine_kernel, carveout)");
+  });
+  if (!ok) return false;
+  CFB_LAUNCH(kern, grid, CFB_ENGINE_THREADS, smem, current_stream(), P);
+  return true;
+}
+static bool launch_real_dispatch(unsigned grid, size_t smem, const EngineParams &P) {
+#define CFB_REAL_CASE(K) \
+  case K: return P.dir < 0 ? launch_real_kernel<K, -1>(grid, smem, P) : launch_real_kernel<K, 1>(grid, smem, P);
+  switch (P.kind) {
+    CFB_REAL_CASE(K_RFFT)
+    CFB_REAL_CASE(K_COST)
+    CFB_REAL_CASE(K_SINT)
+    CFB_REAL_CASE(K_COSQ)
+    CFB_REAL_CASE(K_SINQ)
+    default: break;
+  }
+#undef CFB_REAL_CASE
+  set_error("unknown real family %d", P.kind);
+  return false;
 }
 
 static int log2_ceil_capped(long long v, int cap) {
@@ -140,8 +169,11 @@ static bool launch_engine(EngineParams &P) {
   if (per_sm < 1) per_sm = 1;
   long long grid = per_sm * sm_count();
   if (grid > P.ntiles) grid = P.ntiles;
-  if (real) CFB_LAUNCH(engine_kernel, (unsigned)grid, CFB_ENGINE_THREADS, smem, current_stream(), P);
-  else CFB_LAUNCH(engine_c2c_kernel, (unsigned)grid, CFB_ENGINE_THREADS, smem, current_stream(), P);
+  if (real) {
+    if (!launch_real_dispatch((unsigned)grid, smem, P)) return false;
+  } else {
+    CFB_LAUNCH(engine_c2c_kernel, (unsigned)grid, CFB_ENGINE_THREADS, smem, current_stream(), P);
+  }
   count_launch();
   return cuda_ok(cudaGetLastError(), "engine kernel launch");
 }

@@ -540,11 +540,12 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_c2c_kernel(const
  * complex kernel: the rows of tile k+1 are gathered with 8-byte cp.async while tile k is transformed.
  * Buffers (each T*ldz complex = 2T rows of ldz doubles): B0, B1 alternate as landing buffer; the landing buffer of the
  * current tile becomes the ping-pong partner of A once the pre-processing has consumed the rows. */
+template <bool REV>
 __device__ __forceinline__ void real_issue_loads(const EngineParams &P, double *rowsL, const long long *off_in, int tid,
                                                  int nthr) {
   const double *in = (const double *)P.in;
   const int rows = 2 * P.T, n = P.n, ldz = P.ldz;
-  const bool rev = (P.kind == K_SINQ && P.dir < 0);  // sinqf1_ reverses the sequence first (fftpack.c:14247-14256)
+  const bool rev = REV;  // sinqf1_ reverses the sequence first (fftpack.c:14247-14256)
   const TileWalk w = tile_walk(tid, nthr, P.tx_in_log2, P.ain.lanes_t);
   const long long step = (long long)w.en * P.ain.inc;
   for (int r = w.rs; r < rows; r += w.rn) {
@@ -560,6 +561,7 @@ __device__ __forceinline__ void real_issue_loads(const EngineParams &P, double *
   cp_async_commit();
 }
 
+template <int KIND, int DIR>
 __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const EngineParams P) {
   CFB_DYN_SMEM(smem_raw);
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -585,8 +587,8 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
       off_out[slot * rows + r] = ok ? batch_off(P.aout, g) : -1;
     }
   };
-  const int kind = P.kind, dir = P.dir;
-  const bool fwd_core = !((kind == K_RFFT || kind == K_COSQ || kind == K_SINQ) && dir > 0);
+  constexpr int kind = KIND, dir = DIR;  // compile-time: the family-specific branches below fold away
+  constexpr bool fwd_core = !((kind == K_RFFT || kind == K_COSQ || kind == K_SINQ) && dir > 0);
   // pre/post-processing: the block splits into `groups` groups of gs threads, one row each at a time (rows and the
   // block size are powers of two, so every group makes the same number of trips -- required by the barriers inside)
   const int gs = (nthr / rows) < 32 ? 32 : (nthr / rows), groups = nthr / gs, gid = tid / gs, gl = tid % gs;
@@ -595,14 +597,14 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
   long long tile = blockIdx.x;
   fill_offsets(tile, 0);
   __syncthreads();
-  real_issue_loads(P, (double *)B0, off_in, tid, nthr);
+  real_issue_loads<(KIND == K_SINQ && DIR < 0)>(P, (double *)B0, off_in, tid, nthr);
   int it = 0;
   for (; tile < P.ntiles; tile += gridDim.x, ++it) {
     const int slot = it % 3, nslot = (it + 1) % 3;
     cpx *zB = (it & 1) ? B1 : B0, *Bn = (it & 1) ? B0 : B1;
     fill_offsets(tile + gridDim.x, nslot);
     __syncthreads();  // next offsets visible; the previous tile's storers are done with the other landing buffer
-    real_issue_loads(P, (double *)Bn, off_in + nslot * rows, tid, nthr);
+    real_issue_loads<(KIND == K_SINQ && DIR < 0)>(P, (double *)Bn, off_in + nslot * rows, tid, nthr);
     cp_async_wait<1>();
     __syncthreads();  // rows of this tile have landed
     double *rowsB = (double *)zB, *rowsA = (double *)A;
@@ -654,7 +656,7 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
     {
       double *out = (double *)P.out;
       const long long *oo = off_out + slot * rows;
-      const bool neg_odd = (kind == K_SINQ && dir < 0), rev = (kind == K_SINQ && dir > 0);
+      constexpr bool neg_odd = (kind == K_SINQ && dir < 0), rev = (kind == K_SINQ && dir > 0);
       for (int r = ws.rs; r < rows; r += ws.rn) {
         const long long o = oo[r];
         if (o < 0) continue;
