@@ -252,6 +252,46 @@ static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long lo
   return pow2_tile_launch(a2, dir, P);
 }
 
+/* lengths with a prime factor beyond the four-step split: chirp-z through power-of-two transforms */
+static bool run_c2c_bluestein(int n, long long lot, long long inc, long long jump, int dir, cpx *c, double scale) {
+  const ChirpPlan *cp = get_chirp_plan(n);
+  if (!cp) return false;
+  const int L = cp->L;
+  cpx *z = (cpx *)scratch_get(2, (size_t)lot * L * sizeof(cpx));
+  if (!z) return false;
+  ChirpParams P;
+  memset(&P, 0, sizeof(P));
+  P.n = n;
+  P.L = L;
+  P.dir = dir;
+  P.lot = lot;
+  P.a = make_addr(inc, jump, 0, 1LL << 30);
+  P.user = c;
+  P.z = z;
+  P.chirp = cp->d_chirp;
+  P.bhat = cp->d_bhat;
+  P.scale = scale / (double)L;
+  cudaStream_t st = current_stream();
+  const unsigned gx = (unsigned)((L + 255) / 256 < 256 ? (L + 255) / 256 : 256);
+  const long long YMAX = 65535;
+  int launches = 0;
+  for (P.row0 = 0; P.row0 < lot; P.row0 += YMAX, ++launches)
+    CFB_LAUNCH(chirp_pre_kernel, dim3(gx, (unsigned)(lot - P.row0 < YMAX ? lot - P.row0 : YMAX)), 256, 0, st, P);
+  count_launch(launches);
+  if (!cuda_ok(cudaGetLastError(), "chirp_pre_kernel")) return false;
+  if (!run_c2c_scaled(L, lot, 1, L, -1, z, 1.0)) return false;
+  launches = 0;
+  for (P.row0 = 0; P.row0 < lot; P.row0 += YMAX, ++launches)
+    CFB_LAUNCH(chirp_mul_kernel, dim3(gx, (unsigned)(lot - P.row0 < YMAX ? lot - P.row0 : YMAX)), 256, 0, st, P);
+  count_launch(launches);
+  if (!run_c2c_scaled(L, lot, 1, L, +1, z, 1.0)) return false;
+  launches = 0;
+  for (P.row0 = 0; P.row0 < lot; P.row0 += YMAX, ++launches)
+    CFB_LAUNCH(chirp_post_kernel, dim3(gx, (unsigned)(lot - P.row0 < YMAX ? lot - P.row0 : YMAX)), 256, 0, st, P);
+  count_launch(launches);
+  return cuda_ok(cudaGetLastError(), "chirp kernels");
+}
+
 bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void *c) {
   return run_c2c_scaled(n, lot, inc, jump, dir, c, dir < 0 ? 1.0 / (double)n : 1.0);
 }
@@ -291,10 +331,7 @@ bool run_c2c_scaled(int n, long long lot, long long inc, long long jump, int dir
     if (a1 >= pow2_tile_min_log2() && a2 <= pow2_tile_max_log2()) return run_c2c_pow2_four_step(n, a1, a2, lot, inc, jump, dir, (cpx *)c, scale);
   }
   const int n1 = four_step_split(n, engine_max_c2c());
-  if (n1 <= 1) {
-    set_error("length %d has a prime factor too large for the four-step path", n);
-    return false;
-  }
+  if (n1 <= 1) return run_c2c_bluestein(n, lot, inc, jump, dir, (cpx *)c, scale);  // a prime factor too large to split
   const int n2 = n / n1;
   if (lot * (long long)n2 > 2147483647LL * 16 || lot * (long long)n1 > 2147483647LL * 16) {
     set_error("batch too large");

@@ -756,6 +756,55 @@ __global__ void __launch_bounds__(32) long_post_kernel(const LongRealParams P, i
                 threadIdx.x, 32, nullptr);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Bluestein (chirp-z) kernels for lengths whose prime factors exceed what one CTA or the four-step split can hold:
+ * X_k = c_k * sum_j (x_j c_j) conj(c)_{k-j},  c_j = exp(-+ pi i j^2 / n).  The convolution runs as power-of-two
+ * transforms of length L >= 2n-1 on a scratch array z[lot][L].
+ * ------------------------------------------------------------------------------------------ */
+struct ChirpParams {
+  int n, L, dir;
+  long long lot, row0;
+  Addr a;             // user layout
+  cpx *user;
+  cpx *z;             // [lot][L]
+  const cpx *chirp;   // [n]  forward chirp exp(-pi i j^2 / n)
+  const cpx *bhat;    // [L]  transform of the wrapped conjugate chirp (forward) -- backward uses its conjugate symmetry
+  double scale;
+};
+/* z[row][j] = x[row][j] * c_j (j < n), 0 (n <= j < L) */
+__global__ void __launch_bounds__(256) chirp_pre_kernel(const ChirpParams P) {
+  const long long row = P.row0 + blockIdx.y;
+  const long long off = batch_off(P.a, row);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.L; j += gridDim.x * blockDim.x) {
+    cpx v = make_double2(0.0, 0.0);
+    if (j < P.n) {
+      const cpx x = P.user[off + j * P.a.inc], c = P.chirp[j];
+      v = P.dir < 0 ? cmul(x, c) : cmulc(x, c);
+    }
+    P.z[row * P.L + j] = v;
+  }
+}
+/* z[row][j] *= bhat[j]  (backward: the kernel of the convolution is the conjugate chirp, whose transform is
+ * conj(bhat[(L - j) % L])) */
+__global__ void __launch_bounds__(256) chirp_mul_kernel(const ChirpParams P) {
+  const long long row = P.row0 + blockIdx.y;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.L; j += gridDim.x * blockDim.x) {
+    const cpx b = P.dir < 0 ? P.bhat[j] : P.bhat[(P.L - j) % P.L];
+    cpx *q = P.z + row * P.L + j;
+    *q = P.dir < 0 ? cmul(*q, b) : cmulc(*q, b);
+  }
+}
+/* x[row][k] = z[row][k] * c_k * scale */
+__global__ void __launch_bounds__(256) chirp_post_kernel(const ChirpParams P) {
+  const long long row = P.row0 + blockIdx.y;
+  const long long off = batch_off(P.a, row);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += gridDim.x * blockDim.x) {
+    const cpx v = P.z[row * P.L + k], c = P.chirp[k];
+    cpx y = P.dir < 0 ? cmul(v, c) : cmulc(v, c);
+    P.user[off + k * P.a.inc] = make_double2(y.x * P.scale, y.y * P.scale);
+  }
+}
+
 /* closed forms for the lengths the reference special-cases (costf1_ n=2,3 fftpack.c:6339-6353; sintf1_ n=2
  * :14858-14866; cosqf1_ n=2 :5498-5502; the backward twins) -- one thread per sequence */
 struct TinyParams {

@@ -105,6 +105,7 @@ struct Key {
 std::map<Key, CorePlan *> g_core;
 std::map<Key, TrigPlan *> g_trig;
 std::map<Key, RootPlan *> g_root;
+std::map<Key, ChirpPlan *> g_chirp;
 
 int cur_dev() {
   int d = 0;
@@ -259,6 +260,48 @@ const RootPlan *get_root_plan(int n) {
   return pl;
 }
 
+const ChirpPlan *get_chirp_plan(int n) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Key k{cur_dev(), n, 0};
+    auto it = g_chirp.find(k);
+    if (it != g_chirp.end()) return it->second;
+  }
+  int L = 1;
+  while (L < 2 * n - 1) L *= 2;
+  if (L < 64) L = 64;
+  std::vector<cpx> ch(n), b((size_t)L);
+  for (int j = 0; j < n; ++j) {
+    // exp(-pi i j^2 / n) = exp(-2 pi i (j^2 mod 2n) / (2n)), reduced exactly in integers
+    const long long q = ((long long)j * j) % (2LL * n);
+    unit_root(q, 2LL * n, &ch[j].x, &ch[j].y);
+  }
+  for (auto &v : b) v = make_double2(0.0, 0.0);
+  for (int j = 0; j < n; ++j) {
+    const cpx cj = make_double2(ch[j].x, -ch[j].y);  // conjugate chirp
+    b[j] = cj;
+    if (j > 0) b[L - j] = cj;
+  }
+  ChirpPlan *pl = new ChirpPlan();
+  pl->n = n;
+  pl->L = L;
+  pl->d_chirp = upload(ch);
+  pl->d_bhat = upload(b);
+  if (!pl->d_chirp || !pl->d_bhat) {
+    delete pl;
+    return nullptr;
+  }
+  // transform the kernel once on the device (unscaled forward transform of length L)
+  if (!run_c2c_scaled(L, 1, 1, L, -1, pl->d_bhat, 1.0) || !cuda_ok(cudaStreamSynchronize(current_stream()), "chirp plan")) {
+    delete pl;
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  Key k{cur_dev(), n, 0};
+  g_chirp[k] = pl;
+  return pl;
+}
+
 void release_plans() {
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto &kv : g_core) {
@@ -273,6 +316,12 @@ void release_plans() {
     cudaFree(kv.second->d_w);
     delete kv.second;
   }
+  for (auto &kv : g_chirp) {
+    cudaFree(kv.second->d_chirp);
+    cudaFree(kv.second->d_bhat);
+    delete kv.second;
+  }
+  g_chirp.clear();
   g_core.clear();
   g_trig.clear();
   g_root.clear();

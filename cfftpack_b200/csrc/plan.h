@@ -34,6 +34,13 @@ struct RootPlan {
   cpx *d_w = nullptr;
 };
 
+/* Bluestein plan of length n: chirp c_j = exp(-pi i j^2/n) and the length-L transform of its wrapped conjugate */
+struct ChirpPlan {
+  int n = 0, L = 0;
+  cpx *d_chirp = nullptr, *d_bhat = nullptr;
+};
+const ChirpPlan *get_chirp_plan(int n);
+
 /* Stockham radix schedule used by the engine: 16/8/4/2 for the power of two, then 3, 5, odd primes */
 int engine_factor(int M, int *radix);
 

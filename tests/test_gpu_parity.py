@@ -121,6 +121,15 @@ def test_long_complex_four_step():
     _check_batched("cfft", "f", 4, 1, 16384, 4)
 
 
+def test_large_prime_factors_chirp_z():
+    for n, lot in ((4289, 3), (2 * 4339, 2), (10007, 2), (65537, 1)):
+        extra = 2e-15 * np.log2(n)  # the oracle's own O(p^2) sums are the noisier side for primes this large
+        for d in "fb":
+            _check_batched("cfft", d, lot, n, n, 1, extra=extra)
+    _check_batched("cfft", "f", 3, 1, 4289, 3, extra=3e-14)
+    _check_batched("cost", "f", 2, 8580, 8580, 1, extra=3e-14)  # rfft length 8579 = 23 * 373
+
+
 def test_cfft2_vs_oracle():
     for (ldim, l, m) in ((8, 8, 6), (11, 8, 6), (64, 64, 64), (130, 128, 96), (1024, 1024, 512), (100, 100, 75)):
         c = fl.rand_input("cfft", ldim * m, l + m)

@@ -90,6 +90,17 @@ def test_four_step_long_complex(libs):
         _check(S, O, "cfft", d, 5, 1, 9000, 7)
 
 
+def test_large_prime_factor_uses_chirp_z(libs):
+    """a prime factor beyond one CTA and beyond the four-step split (4289 is prime): Bluestein on power-of-two transforms"""
+    S, O = libs
+    nmax = fl.sim().cfb200_max_onchip_complex()
+    assert 4289 > nmax
+    for d in "fb":
+        _check(S, O, "cfft", d, 2, 4289, 4289, 1)
+        _check(S, O, "cfft", d, 2, 1, 4289, 2)
+    _check(S, O, "rfft", "f", 2, 2 * 4289, 2 * 4289, 1)  # long real path -> complex length with the same prime
+
+
 def test_cfft2(libs):
     S, O = libs
     for (ldim, l, m) in ((8, 8, 6), (11, 8, 6), (64, 64, 64), (130, 128, 96)):
