@@ -207,6 +207,7 @@ static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long lo
   P.fs = rp->d_w;
   P.fs_shift = rp->shift;
   P.fs_count = (1 << rp->shift) + (n + (1 << rp->shift) - 1) / (1 << rp->shift);
+  P.fs_nmask = n - 1;
   if (!batch_fast) {  // row g = m*n2 + j2 (j2 fast); scratch S[m][k1][j2]
     P.ain = make_addr((long long)n2 * inc, inc, jump, n2);
     P.aout = make_addr(n2, 1, n, n2);

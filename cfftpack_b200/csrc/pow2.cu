@@ -202,8 +202,36 @@ bool launch_r2c(long long lot, long long jump, double *r) {
   return launch_r2c_stream<Pow2Cfg<LOG2N>, StreamMinB<LOG2N>::value, DIR>(lot, jump, r);
 }
 
+/* streaming tile kernel (default); CFB200_TILE_DIRECT=1 selects the direct-load one for comparison */
+template <int LOG2N, int DIR, int THREADS = 256>
+bool launch_tile_stream(TileParams &P) {
+  typedef Pow2Cfg<LOG2N, 4, 1, THREADS> C;
+  P.tw = pow2_stream_table<C>();
+  if (!P.tw) return false;
+  static std::once_flag once;
+  static bool ok = true;
+  auto kern = pow2_tile_stream_kernel<C, DIR>;
+  if (!set_smem_once(kern, SMEM_LIMIT, once, ok)) return false;
+  const size_t smem = TileStreamSmem<C>::bytes(P.fs_count);
+  if (smem > SMEM_LIMIT) return false;
+  const long long ntiles = (P.lot + C::TPB - 1) / C::TPB;
+  long long per_sm = (long long)((SMEM_LIMIT + 1024) / (smem + 1024));
+  if (per_sm > (C::THREADS > 256 ? 1 : 2)) per_sm = (C::THREADS > 256 ? 1 : 2);
+  if (per_sm < 1) per_sm = 1;
+  long long grid = per_sm * sm_count();
+  if (grid > ntiles) grid = ntiles;
+  CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, smem, current_stream(), P, ntiles);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "pow2_tile_stream_kernel launch");
+}
+
 template <int LOG2N, int DIR>
 bool launch_tile(TileParams &P) {
+  static const bool direct = getenv("CFB200_TILE_DIRECT") != nullptr;
+  static const bool wide = getenv("CFB200_TILE_WIDE") != nullptr;  // experiment: 512-thread CTAs, twice the rows per tile
+  if (wide && LOG2N <= 7 && TileStreamSmem<Pow2Cfg<LOG2N, 4, 1, 512>>::bytes(P.fs_count) <= SMEM_LIMIT)
+    return launch_tile_stream<(LOG2N <= 7 ? LOG2N : 7), DIR, 512>(P);
+  if (!direct && TileStreamSmem<Pow2Cfg<LOG2N, 4, 1>>::bytes(P.fs_count) <= SMEM_LIMIT) return launch_tile_stream<LOG2N, DIR>(P);
   typedef Pow2Cfg<LOG2N, 4, 0> C;
   P.tw = pow2_table<C>();
   if (!P.tw) return false;

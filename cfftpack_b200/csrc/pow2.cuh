@@ -28,14 +28,14 @@ namespace cfb {
 
 /* LP = log2(points per thread); TW = 1: the twiddles of a stage with many distinct values are rebuilt in
  * registers from two table entries (w^p, w^4p) instead of P-1 loads (keeps the tables L1-resident) */
-template <int LOG2N, int LP_ = ((LOG2N >= 8) ? 4 : 3), int TW_ = 1>
+template <int LOG2N, int LP_ = ((LOG2N >= 8) ? 4 : 3), int TW_ = 1, int MINTHREADS_ = 256>
 struct Pow2Cfg {
   static constexpr int N = 1 << LOG2N;
   static constexpr int LP = LP_;
   static constexpr int TW = TW_;
   static constexpr int P = 1 << LP;
   static constexpr int NT = N / P;                 // threads per sequence
-  static constexpr int THREADS = (NT > 256) ? NT : 256;
+  static constexpr int THREADS = (NT > MINTHREADS_) ? NT : MINTHREADS_;
   static constexpr int TPB = THREADS / NT;         // sequences (or pairs) per CTA
   static constexpr int NFULL = LOG2N / LP;
   static constexpr int REM = LOG2N % LP;
@@ -261,7 +261,7 @@ __device__ __forceinline__ int xpad(int e) {
   return e + StreamSmem<C>::PADW * (e >> C::LP);
 }
 
-template <class C, int DIR>
+template <class C, int DIR, bool VEC0 = true>
 __device__ __forceinline__ void pow2_core_split(cpx (&a)[C::P], double *__restrict__ xr, const int t,
                                                 const cpx *__restrict__ tws) {
   constexpr int P = C::P, LP = C::LP, NT = C::NT;
@@ -277,7 +277,7 @@ __device__ __forceinline__ void pow2_core_split(cpx (&a)[C::P], double *__restri
       const cpx *twp = tws + S::tws_offset(st) + p;
       twiddle_powers<DIR>(a, twp[0], twp[m]);
       const int base = q + s * P * p;
-      if (st == 0 && S::PADW == 2) {
+      if (VEC0 && st == 0 && S::PADW == 2) {
         // first exchange: a thread's P outputs are adjacent -> 16-byte stores (row pitch P+2 keeps them aligned)
         double2 *row = (double2 *)(xr + xpad<C>(base));
 #pragma unroll
@@ -290,7 +290,7 @@ __device__ __forceinline__ void pow2_core_split(cpx (&a)[C::P], double *__restri
 #pragma unroll
       for (int i = 0; i < P; ++i) a[i].x = xr[xpad<C>(t + NT * i)];
       __syncthreads();
-      if (st == 0 && S::PADW == 2) {
+      if (VEC0 && st == 0 && S::PADW == 2) {
         double2 *row = (double2 *)(xr + xpad<C>(base));
 #pragma unroll
         for (int k = 0; k < P; k += 2) row[k / 2] = make_double2(a[k].y, a[k + 1].y);
@@ -492,6 +492,7 @@ struct TileParams {
   const cpx *tw;  // pow2_table of the row length
   const cpx *fs;  // split twiddle tables of the long length (nullptr: none)
   int fs_shift, fs_from_hi, fs_count;
+  int fs_nmask;   // long length - 1 (a power of two)
   int in_staged;  // 1: rows are contiguous along the element axis on the input side
   // sharded 2-D transform: the transform axis of the OUTPUT is split over npeers GPUs in chunks of 2^peer_shift
   // elements; element e goes to peers[e >> peer_shift] (a peer-mapped pointer, NVLink store) at local index
@@ -590,6 +591,125 @@ __global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_kernel(const TilePara
       for (int i = 0; i < PP; ++i) y[i * st] = make_double2(a[i].x * scale, a[i].y * scale);
     }
   }
+}
+
+/* Streaming form of the tile kernel: persistent CTAs; the rows of tile k+1 are gathered with per-thread cp.async
+ * (16 bytes per element, whichever thread order is coalesced for the layout) into a landing buffer while tile k is
+ * transformed.  The landing buffer doubles as the transposition stage, so both row layouts take the same path. */
+template <class C>
+struct TileStreamSmem {
+  typedef StreamSmem<C> S;
+  static constexpr int LPITCH = C::N + 1;          // landing rows, complex; odd pitch for rows-fastest readers
+  static constexpr int XPITCH = S::XTILE | 1;      // exchange rows, doubles
+  static constexpr size_t LAND = (size_t)C::TPB * LPITCH * sizeof(cpx);
+  static constexpr size_t XCH = (size_t)C::TPB * XPITCH * sizeof(double);
+  static constexpr size_t TWS = S::TWS;
+  static constexpr size_t bytes(int fs_count) {
+    return LAND + XCH + TWS + (size_t)2 * C::TPB * 8 + (size_t)fs_count * sizeof(cpx) + 64;
+  }
+};
+
+template <class C>
+__device__ __forceinline__ void tile_issue_loads(const TileParams &P, cpx *land, long long *rowoff, long long tile,
+                                                 int tid) {
+  constexpr int N = C::N, NT = C::NT, TPB = C::TPB, PP = C::P, LPITCH = TileStreamSmem<C>::LPITCH;
+  if (!P.in_staged) {  // rows are the contiguous axis: thread (row tl, slot t) fetches its own P elements
+    const int tl = tid % TPB, t = tid / TPB;
+    const long long g = tile * TPB + tl;
+    if (g < P.lot) {
+      const cpx *x = P.in + tile_batch_off(P.ain, g) + (long long)t * P.ain.inc;
+      const long long st = (long long)NT * P.ain.inc;
+      cpx *row = land + (size_t)tl * LPITCH + t;
+#pragma unroll
+      for (int i = 0; i < PP; ++i) cp_async16(row + NT * i, x + i * st);
+    }
+  } else {  // rows are contiguous along the element axis: consecutive threads walk one row
+    for (int idx = tid; idx < TPB * N; idx += C::THREADS) {
+      const int r = idx / N, e = idx % N;
+      const long long o = rowoff[r];
+      if (o >= 0) cp_async16(land + (size_t)r * LPITCH + e, P.in + o + (long long)e * P.ain.inc);
+    }
+  }
+  cp_async_commit();
+}
+
+template <class C, int DIR>
+__global__ void __launch_bounds__(C::THREADS, (C::THREADS > 256 ? 1 : 2)) pow2_tile_stream_kernel(const TileParams P, long long ntiles) {
+  CFB_DYN_SMEM(smem_raw);
+  typedef TileStreamSmem<C> TS;
+  typedef StreamSmem<C> S;
+  constexpr int PP = C::P, NT = C::NT, TPB = C::TPB;
+  cpx *land = (cpx *)smem_raw;
+  double *xch = (double *)(smem_raw + TS::LAND);
+  cpx *tws = (cpx *)(smem_raw + TS::LAND + TS::XCH);
+  long long *rowoff = (long long *)(smem_raw + TS::LAND + TS::XCH + TS::TWS);  // [2][TPB] (staged input only)
+  cpx *fss = (cpx *)(rowoff + 2 * TPB);
+  const int tid = threadIdx.x, tl = tid % TPB, t = tid / TPB;
+  for (int i = tid; i < S::TWS_COUNT; i += C::THREADS) tws[i] = __ldg(P.tw + i);
+  for (int i = tid; i < P.fs_count; i += C::THREADS) fss[i] = __ldg(P.fs + i);
+  auto fill_rowoff = [&](long long tile, int slot) {
+    if (P.in_staged && tid < TPB) {
+      const long long g = tile * TPB + tid;
+      rowoff[slot * TPB + tid] = (tile < ntiles && g < P.lot) ? tile_batch_off(P.ain, g) : -1;
+    }
+  };
+  long long tile = blockIdx.x;
+  fill_rowoff(tile, 0);
+  __syncthreads();
+  if (tile < ntiles) tile_issue_loads<C>(P, land, rowoff, tile, tid);
+  else cp_async_commit();
+  double *xr = xch + (size_t)tl * TS::XPITCH;
+  const cpx *lrow = land + (size_t)tl * TS::LPITCH;
+  int it = 0;
+  for (; tile < ntiles; tile += gridDim.x, ++it) {
+    const long long g = tile * TPB + tl;
+    const bool live = g < P.lot;
+    cp_async_wait<0>();
+    __syncthreads();  // the tile has landed for every thread
+    cpx a[PP];
+#pragma unroll
+    for (int i = 0; i < PP; ++i) a[i] = lrow[t + NT * i];
+    const long long next = tile + gridDim.x;
+    fill_rowoff(next, (it + 1) & 1);
+    __syncthreads();  // landing buffer consumed (and next row offsets visible): refill it while we compute
+    if (next < ntiles) tile_issue_loads<C>(P, land, rowoff + ((it + 1) & 1) * TPB, next, tid);
+    else cp_async_commit();
+    pow2_core_split<C, DIR, false>(a, xr, t, tws);
+    if (live) {
+      const long long oout = tile_batch_off(P.aout, g);
+      const double scale = P.scale;
+      if (P.npeers > 0) {
+        const int emask = (1 << P.peer_shift) - 1;
+#pragma unroll
+        for (int i = 0; i < PP; ++i) {
+          const int e = t + NT * i;
+          cpx *dst = P.peers[e >> P.peer_shift] + P.out_base + oout + (long long)(e & emask) * P.aout.inc;
+          *dst = make_double2(a[i].x * scale, a[i].y * scale);
+        }
+      } else {
+        cpx *y = P.out + oout + (long long)t * P.aout.inc;
+        const long long st = (long long)NT * P.aout.inc;
+        if (P.fs_count > 0) {
+          // four-step twiddles W_n^(j (t + NT i)) = base * step^i: base, step and step^4 from the split tables
+          // (six shared-memory reads instead of two per element), the powers as in twiddle_powers
+          const int j = (int)(P.fs_from_hi ? g / P.aout.nlo : g % P.aout.nlo);
+          const int mask = (1 << P.fs_shift) - 1, sh = P.fs_shift, nmask = P.fs_nmask;
+          auto root = [&](int x) { return cmul(fss[x & mask], fss[mask + 1 + (x >> sh)]); };
+          const cpx base = root(j * t), w1 = root((j * NT) & nmask), w4 = root((4 * j * NT) & nmask);
+          cpx b[PP];
+#pragma unroll
+          for (int i = 0; i < PP; ++i) b[i] = base;
+          twiddle_powers<-1>(b, w1, w4);  // b[i] = base * w1^i (i >= 1)
+#pragma unroll
+          for (int i = 0; i < PP; ++i) y[i * st] = ctw<DIR>(make_double2(a[i].x * scale, a[i].y * scale), b[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < PP; ++i) y[i * st] = make_double2(a[i].x * scale, a[i].y * scale);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
 }
 
 /* ---- host side ---- */

@@ -67,7 +67,9 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
                : "memory");
 }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+  // .ca: the two 16-byte halves of a 32-byte sector requested by neighbouring lanes merge in L1 (with .cg every
+  // 16-byte request fetched its own sector from L2: 2x read amplification measured)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
