@@ -159,7 +159,7 @@ def run_reference(args, fam, n, lot, rank, world):
     orc.orc_lot_parallel.restype = ctypes.c_double
     orc.orc_lot_parallel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
-    slot = 256 * threads
+    slot = 1024 * threads  # sequences per step: large enough that thread start-up is amortised (~1 GiB at 16 threads)
     x = fl.rand_input(fam, slot * n, 11)
     is_c = 1 if fam == "cfft" else 0
     for _ in range(args.warmup):
