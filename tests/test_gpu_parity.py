@@ -398,3 +398,28 @@ def test_repeatability_and_sampled_parity_at_full_occupancy():
             idx = mrow * jump + inc * np.arange(n)
             want, ier = ORC.run1(fam, "f", n, host_in[idx])
             assert fl.rel_l2(host_out[idx], want) <= fl.tol(n), (fam, n, lot, mrow)
+
+
+def test_reference_option_pricing_demo_relinked():
+    """test/vargamma.c (Carr-Madan style rfft convolution pricing, N = 128 ... 2^20; the workload behind BASELINE
+    config 3) built against libcfftpack_b200.so prints the same prices as the all-reference build, and reproduces the
+    known answers of SURVEY 8(c): Black-Scholes 8.779874623570, QuantLib variance-gamma target 9.3424659413582116."""
+    import os
+    import re
+    import subprocess
+    a_exe = os.path.join(fl.ROOT, "oracle", "_ref", "vargamma_b200")
+    b_exe = os.path.join(fl.ROOT, "oracle", "_ref", "vargamma_ref")
+    if not (os.path.exists(a_exe) and os.path.exists(b_exe)):
+        pytest.skip("oracle/_ref/vargamma_* not prebuilt")
+    a = subprocess.run([a_exe], capture_output=True, text=True, timeout=600).stdout
+    b = subprocess.run([b_exe], capture_output=True, text=True, timeout=600).stdout
+    rows = lambda s: [(int(m.group(1)), float(m.group(2))) for m in re.finditer(r"^\s*(\d+)\s+(-?\d+\.\d{12})\s", s, re.M)]
+    ra, rb = rows(a), rows(b)
+    assert len(ra) == len(rb) == 28, (len(ra), len(rb), a[-500:])
+    for (na, pa), (nb, pb) in zip(ra, rb):
+        assert na == nb and abs(pa - pb) <= 1e-9 * max(1.0, abs(pb)), (na, pa, pb)
+    assert "Black Scholes Formula: 8.779874623570" in a
+    bs_4096 = [p for n, p in ra[:14] if n == 4096][0]
+    assert abs(bs_4096 - 8.779878465793) < 1e-9
+    vg_last = ra[-1][1]
+    assert abs(vg_last - 9.3424659413582116) < 2e-5
