@@ -122,7 +122,6 @@ static bool launch_engine(EngineParams &P) {
   }
   const int longest = P.M > P.n ? P.M : P.n;
   P.ldz = (longest + ((longest - 1) >> P.padshift) + 1) | 1;
-  P.ldx = 0;
   // bytes per sequence (c2c: three complex rows -- two landing buffers + the ping-pong partner -- and double-buffered
   // row tables) or per pair (real kinds: two complex rows and the row tables)
   const size_t per = real ? (size_t)P.ldz * 48 + 256 : (size_t)P.ldz * 48 + 64;

@@ -150,18 +150,6 @@ __device__ __forceinline__ long long batch_off(const Addr &a, long long g) {
   return hi * a.jump_hi + lo * a.jump_lo;
 }
 
-/* split a linear work index over a [rows][len] tile so that consecutive threads follow the axis that is
- * contiguous in global memory */
-__device__ __forceinline__ void tile_index(int idx, int rows, int len, int lanes_t, int &row, int &e) {
-  if (lanes_t) {
-    e = idx / rows;
-    row = idx - e * rows;
-  } else {
-    row = idx / len;
-    e = idx - row * len;
-  }
-}
-
 /* ---- warp helpers (one warp works on one real sequence in the pre/post phases) ---- */
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -394,22 +382,6 @@ __device__ __forceinline__ void post_sequence(int kind, int dir, int n, int M, c
     }
   }
 }
-
-/* ------------------------------------------------------------------------------------------ */
-/* loader / storer tiling: 2^txl threads walk the axis that is contiguous in global memory (elements when
- * lanes_t == 0, rows when lanes_t == 1), the remaining threads walk the other axis.  No divisions. */
-#define CFB_TILE_LOOP(ROWS, LEN, LANES_T, TXL, BODY)                                   \
-  {                                                                                    \
-    const int tx_ = tid & ((1 << (TXL)) - 1), ty_ = tid >> (TXL);                      \
-    const int nx_ = 1 << (TXL), ny_ = nthr >> (TXL);                                   \
-    if (LANES_T) {                                                                     \
-      for (int e = ty_; e < (LEN); e += ny_)                                           \
-        for (int r = tx_; r < (ROWS); r += nx_) BODY                                   \
-    } else {                                                                           \
-      for (int r = ty_; r < (ROWS); r += ny_)                                          \
-        for (int e = tx_; e < (LEN); e += nx_) BODY                                    \
-    }                                                                                  \
-  }
 
 /* complex sequences, software-pipelined: while tile k is transformed, tile k+1 is gathered from global memory into
  * a second landing buffer with per-thread asynchronous copies (cp.async / LDGSTS), so the long global-load latency

@@ -37,7 +37,6 @@ struct EngineParams {
   int nf;
   int T;    // complex sequences (c2c) or PAIRS of real sequences (other kinds) per CTA
   int ldz;  // row pitch of the complex buffers (odd, >= max(M, n)); real rows use the same pitch in doubles
-  int ldx;  // unused (kept for layout stability)
   int tx_in_log2, tx_out_log2;  // loader / storer thread tiling: 2^tx threads walk the contiguous axis
   int padshift;                 // shared-memory rows get one pad slot every 2^padshift elements (31 = none)
   int tw_smem;                  // > 0: number of plan twiddles copied to shared memory by each CTA

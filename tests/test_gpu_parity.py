@@ -423,3 +423,21 @@ def test_reference_option_pricing_demo_relinked():
     assert abs(bs_4096 - 8.779878465793) < 1e-9
     vg_last = ra[-1][1]
     assert abs(vg_last - 9.3424659413582116) < 2e-5
+
+
+def test_sharded_cfft2_two_gpus_fused_p2p_vs_nccl():
+    """needs >= 2 GPUs (skipped on single-GPU boxes): the FFT+transpose fused path (P2P stores into peer slabs) must
+    equal the NCCL all-to-all path bit for bit and invert itself"""
+    import json
+    import os
+    import subprocess
+    import sys
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("single GPU")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29547",
+                          os.path.join(fl.ROOT, "tools", "run_dist2d.py"), "4096"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    j = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert j["p2p_vs_nccl_rel_err"] == 0.0 and j["p2p_roundtrip_rel_err"] <= fl.tol(4096 * 4096), j
