@@ -146,6 +146,7 @@ __device__ __forceinline__ void run_passes(cpx *&cur, cpx *&oth, const EnginePar
 }
 
 __device__ __forceinline__ long long batch_off(const Addr &a, long long g) {
+  if (a.jump_hi == 0) return g * a.jump_lo;  // single-level batch (no 64-bit division)
   long long hi = g / a.nlo, lo = g - hi * a.nlo;
   return hi * a.jump_hi + lo * a.jump_lo;
 }
@@ -219,19 +220,6 @@ __device__ __forceinline__ double group_sum(double v, int gl, int gs, double *gs
   }
   return v;
 }
-/* exclusive prefix of v over the threads of the group */
-__device__ __forceinline__ double group_excl_scan(double v, int gl, int gs, double *gsc) {
-  const int lane = gl & 31;
-  const double ex = warp_excl_scan(v, lane);
-  if (gs <= 32) return ex;
-  const double tot = __shfl_sync(0xffffffffu, ex + v, 31);
-  if (lane == 0) gsc[gl >> 5] = tot;
-  __syncthreads();
-  double carry = 0.0;
-  for (int w = 0; w < (gl >> 5); ++w) carry += gsc[w];
-  return carry + ex;
-}
-
 /* x: the loaded sequence (length n, unit stride).  Forward-core kinds write u (length M) into the re or im
  * lane of the complex row (zc, stride 2).  Backward-core kinds write the half-complex row h (unit stride). */
 __device__ __forceinline__ void pre_forward_core(int kind, int dir, int n, int M, const double *__restrict__ x,
@@ -319,39 +307,63 @@ __device__ __forceinline__ void post_sequence(int kind, int dir, int n, int M, c
     const double D = dir < 0 ? dsum / (double)M : 0.5 * dsum;
     const int last = (M % 2 == 0) ? M - 1 : -1;
     const int cnt = n / 2;  // odd output indices 2m-1, m = 1..cnt
-    const int chunk = (cnt + gs - 1) / gs;
-    const int m_lo = 1 + gl * chunk, m_hi = min(m_lo + chunk, cnt + 1);
-    double loc = 0.0;  // sum over my m of c1*h'[2m]
-    for (int mm = m_lo; mm < m_hi; ++mm) {
-      int i = 2 * mm;
-      if (i < M) loc += c1 * (i == last ? 2.0 * s[i] : s[i]);
+    // exclusive prefix over m of v(m) = c1 h'[2m]: each warp of the group owns a contiguous segment of m and walks it
+    // 32 at a time (lane-interleaved: conflict-free shared-memory access); segment totals give the carry-in
+    auto val = [&](int mm) -> double {
+      const int i = 2 * mm;
+      return (mm <= cnt && i < M) ? c1 * (i == last ? 2.0 * s[i] : s[i]) : 0.0;
+    };
+    const int nw = gs >> 5, w = gl >> 5, lane = gl & 31;
+    const int seg = ((cnt + nw - 1) / nw + 31) & ~31;  // segment length per warp, a multiple of 32
+    const int m0 = 1 + w * seg;
+    double carry = D;
+    if (nw > 1) {
+      double tot = 0.0;
+      for (int mm = m0 + lane; mm < m0 + seg; mm += 32) tot += val(mm);
+      tot = warp_sum(tot);
+      if (lane == 0) gsc[w] = tot;
+      __syncthreads();
+      for (int w2 = 0; w2 < w; ++w2) carry += gsc[w2];
     }
-    double run = D + group_excl_scan(loc, gl, gs, gsc);
-    for (int mm = m_lo; mm < m_hi; ++mm) {
-      int i = 2 * mm;
-      y[i - 1] = run;
-      if (i < M) run += c1 * (i == last ? 2.0 * s[i] : s[i]);
-      if (i < n) y[i] = c1 * ((i - 1) == last ? 2.0 * s[i - 1] : s[i - 1]);
+    for (int base = m0; base < m0 + seg && base <= cnt; base += 32) {
+      const int mm = base + lane;
+      const double v = val(mm);
+      const double ex = warp_excl_scan(v, lane);
+      if (mm <= cnt) {
+        const int i = 2 * mm;
+        y[i - 1] = carry + ex;
+        if (i < n) y[i] = c1 * ((i - 1) == last ? 2.0 * s[i - 1] : s[i - 1]);
+        if (dir < 0 && mm == cnt) y[n - 1] *= 0.5;  // y[n-1] is y[2cnt-1] (n even) or y[2cnt] (n odd): mine
+      }
+      carry += __shfl_sync(0xffffffffu, ex + v, 31);
     }
-    // y[0] and (forward) the halving of y[n-1]: done by the thread that produced y[n-1]
     if (gl == 0) y[0] = c0 * s[0];
-    if (dir < 0) {
-      const int owner_m = (n - 1 + 1) / 2;  // y[n-1] is written in iteration mm = ceil((n-1)/2) (as y[2mm-1] or y[2mm])
-      if (owner_m >= m_lo && owner_m < m_hi) y[n - 1] *= 0.5;
-    }
   } else if (kind == K_SINT) {
     // sintf1_ post (fftpack.c:14898-14919): y[2m] = sc h[0] + sum_{m'<=m} sc h[2m'-1]; y[2m-1] = sc h[2m]
     const double sc = dir < 0 ? 0.5 : 0.25 * (double)M;
     const int cnt = (n - 1) / 2;  // even output indices 2m, m = 1..cnt
-    const int chunk = (cnt + gs - 1) / gs;
-    const int m_lo = 1 + gl * chunk, m_hi = min(m_lo + chunk, cnt + 1);
-    double loc = 0.0;
-    for (int mm = m_lo; mm < m_hi; ++mm) loc += sc * s[2 * mm - 1];
-    double run = sc * s[0] + group_excl_scan(loc, gl, gs, gsc);
-    for (int mm = m_lo; mm < m_hi; ++mm) {
-      run += sc * s[2 * mm - 1];
-      y[2 * mm] = run;
-      y[2 * mm - 1] = sc * s[2 * mm];
+    auto val = [&](int mm) -> double { return mm <= cnt ? sc * s[2 * mm - 1] : 0.0; };
+    const int nw = gs >> 5, w = gl >> 5, lane = gl & 31;
+    const int seg = ((cnt + nw - 1) / nw + 31) & ~31;
+    const int m0 = 1 + w * seg;
+    double carry = sc * s[0];
+    if (nw > 1) {
+      double tot = 0.0;
+      for (int mm = m0 + lane; mm < m0 + seg; mm += 32) tot += val(mm);
+      tot = warp_sum(tot);
+      if (lane == 0) gsc[w] = tot;
+      __syncthreads();
+      for (int w2 = 0; w2 < w; ++w2) carry += gsc[w2];
+    }
+    for (int base = m0; base < m0 + seg && base <= cnt; base += 32) {
+      const int mm = base + lane;
+      const double v = val(mm);
+      const double ex = warp_excl_scan(v, lane);
+      if (mm <= cnt) {
+        y[2 * mm] = carry + ex + v;
+        y[2 * mm - 1] = sc * s[2 * mm];
+      }
+      carry += __shfl_sync(0xffffffffu, ex + v, 31);
     }
     if (gl == 0) {
       y[0] = sc * s[0];
