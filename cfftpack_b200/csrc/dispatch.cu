@@ -22,7 +22,7 @@ namespace cfb {
 static const size_t SMEM_MAX = 227 * 1024;      // opt-in limit per CTA on sm_100
 static const size_t SMEM_TARGET = 72 * 1024;    // aim: three CTAs per SM for the streaming kernels
 
-int engine_max_c2c() { return (int)((SMEM_MAX - 1024) / 48 * 8 / 9) - 2; }
+int engine_max_c2c() { return (int)((SMEM_MAX - 1024) / 48) - 4; }
 int engine_max_real() { return (int)((SMEM_MAX - 1024) / 48) - 4; }
 
 static bool engine_attr_once() {
@@ -122,6 +122,10 @@ static bool launch_engine(EngineParams &P) {
   }
   const int longest = P.M > P.n ? P.M : P.n;
   P.ldz = (longest + ((longest - 1) >> P.padshift) + 1) | 1;
+  if (!real && (size_t)P.ldz * 48 + 64 + 64 + (size_t)(P.tw_smem + P.fs_smem) * sizeof(cpx) > SMEM_MAX) {
+    P.padshift = 31;  // a long sequence that only fits without the padding slots
+    P.ldz = (longest + 1) | 1;
+  }
   // bytes per sequence (c2c: three complex rows -- two landing buffers + the ping-pong partner -- and double-buffered
   // row tables) or per pair (real kinds: two complex rows and the row tables)
   const size_t per = real ? (size_t)P.ldz * 48 + 256 : (size_t)P.ldz * 48 + 64;

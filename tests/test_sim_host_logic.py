@@ -91,14 +91,23 @@ def test_four_step_long_complex(libs):
 
 
 def test_large_prime_factor_uses_chirp_z(libs):
-    """a prime factor beyond one CTA and beyond the four-step split (4289 is prime): Bluestein on power-of-two transforms"""
+    """a prime factor beyond one CTA and beyond the four-step split (4831 is prime): Bluestein on power-of-two transforms"""
     S, O = libs
     nmax = fl.sim().cfb200_max_onchip_complex()
-    assert 4289 > nmax
+    assert 4831 > nmax
     for d in "fb":
-        _check(S, O, "cfft", d, 2, 4289, 4289, 1)
-        _check(S, O, "cfft", d, 2, 1, 4289, 2)
-    _check(S, O, "rfft", "f", 2, 2 * 4289, 2 * 4289, 1)  # long real path -> complex length with the same prime
+        _check(S, O, "cfft", d, 2, 4831, 4831, 1)
+        _check(S, O, "cfft", d, 2, 1, 4831, 2)
+    _check(S, O, "rfft", "f", 2, 2 * 4831, 2 * 4831, 1)  # long real path -> complex length with the same prime
+
+
+def test_longest_on_chip_complex_lengths(libs):
+    """lengths just below the single-CTA limit (padded rows no longer fit and are dropped), incl. a prime"""
+    S, O = libs
+    nmax = fl.sim().cfb200_max_onchip_complex()
+    for n in (4000, 4096 + 512, nmax - 1, nmax):
+        inc = 2 if n == 4000 else 1
+        _check(S, O, "cfft", "f", 2, n * inc + 3, n, inc)
 
 
 def test_cfft2(libs):
@@ -171,3 +180,26 @@ print('ok')
     env = dict(os.environ, CFB200_LONG_REAL_MIN="20")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-500:] + out.stderr[-2000:]
+
+
+def test_randomized_shapes_small(libs):
+    """the same randomized sweep as the GPU test, at sizes the emulator handles quickly"""
+    S, O = libs
+    rng = np.random.default_rng(42)
+    lengths = [2, 3, 4, 5, 6, 7, 9, 10, 12, 14, 15, 18, 21, 25, 27, 33, 36, 45, 49, 50, 63, 64, 70, 81, 90, 98, 100, 121, 128, 143,
+               169, 180, 200, 243, 256, 300, 343, 360, 512, 625, 1000, 1024]
+    for case in range(60):
+        fam = fl.FAMILIES[int(rng.integers(len(fl.FAMILIES)))]
+        n = int(lengths[int(rng.integers(len(lengths)))])
+        lot = int(rng.choice([1, 2, 3, 5, 8, 9, 16, 17]))
+        layout = int(rng.integers(4))
+        if layout == 0:
+            inc, jump = 1, n
+        elif layout == 1:
+            inc, jump = 1, n + int(rng.integers(1, 9))
+        elif layout == 2:
+            inc, jump = lot, 1
+        else:
+            inc = int(rng.integers(2, 5))
+            jump = inc * (n - 1) + 1 + int(rng.integers(0, 7))
+        _check(S, O, fam, "fb"[int(rng.integers(2))], lot, jump, n, inc, seed=case)
