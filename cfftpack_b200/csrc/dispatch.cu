@@ -71,7 +71,7 @@ static int four_step_split(int n, int limit) {
 
 /* the real-family kernel is instantiated per (family, direction): the family-specific code folds at compile time */
 template <int KIND, int DIR>
-static bool launch_real_kernel(unsigned grid, size_t smem, const EngineParams &P) {
+static bool launch_real_kernel(unsigned grid, unsigned threads, size_t smem, const EngineParams &P) {
   static std::once_flag once;
   static bool ok = true;
   auto kern = engine_kernel<KIND, DIR>;
@@ -82,12 +82,12 @@ static bool launch_real_kernel(unsigned grid, size_t smem, const EngineParams &P
                  "cudaFuncSetAttribute(engine_kernel, carveout)");
   });
   if (!ok) return false;
-  CFB_LAUNCH(kern, grid, CFB_ENGINE_THREADS, smem, current_stream(), P);
+  CFB_LAUNCH(kern, grid, threads, smem, current_stream(), P);
   return true;
 }
-static bool launch_real_dispatch(unsigned grid, size_t smem, const EngineParams &P) {
+static bool launch_real_dispatch(unsigned grid, unsigned threads, size_t smem, const EngineParams &P) {
 #define CFB_REAL_CASE(K) \
-  case K: return P.dir < 0 ? launch_real_kernel<K, -1>(grid, smem, P) : launch_real_kernel<K, 1>(grid, smem, P);
+  case K: return P.dir < 0 ? launch_real_kernel<K, -1>(grid, threads, smem, P) : launch_real_kernel<K, 1>(grid, threads, smem, P);
   switch (P.kind) {
     CFB_REAL_CASE(K_RFFT)
     CFB_REAL_CASE(K_COST)
@@ -163,19 +163,25 @@ static bool launch_engine(EngineParams &P) {
   P.T = (int)T;
   const long long rows = real ? 2 * T : T;
   // thread tiling of the loader/storer: threads along the contiguous axis first
-  P.tx_in_log2 = log2_ceil_capped(P.ain.lanes_t ? rows : len, 8);
-  P.tx_out_log2 = log2_ceil_capped(P.aout.lanes_t ? rows : len, 8);
+  P.tx_in_log2 = log2_ceil_capped(P.ain.lanes_t ? rows : len, 7);
+  P.tx_out_log2 = log2_ceil_capped(P.aout.lanes_t ? rows : len, 7);
   const size_t smem = per * (size_t)T + fixed;
   P.ntiles = (units + T - 1) / T;
+  // block size: 128 threads when a tile has too little work per pass for 256 (small T x M): more CTAs per SM instead
+  static const int force_threads = getenv("CFB200_ENGINE_THREADS") ? atoi(getenv("CFB200_ENGINE_THREADS")) : 0;
+  unsigned threads = CFB_ENGINE_THREADS;
+  if (!real && (long long)T * P.M <= 1280) threads = 128;  // measured: helps the complex kernel slightly, hurts the real one
+  if (force_threads == 128 || force_threads == 256) threads = (unsigned)force_threads;
   long long per_sm = (long long)((SMEM_MAX + 1024) / (smem + 1024));
-  if (per_sm > 3) per_sm = 3;  // register-limited (launch bounds)
+  const long long reg_limit = threads == 128 ? 6 : 3;  // 80 registers per thread (launch bounds)
+  if (per_sm > reg_limit) per_sm = reg_limit;
   if (per_sm < 1) per_sm = 1;
   long long grid = per_sm * sm_count();
   if (grid > P.ntiles) grid = P.ntiles;
   if (real) {
-    if (!launch_real_dispatch((unsigned)grid, smem, P)) return false;
+    if (!launch_real_dispatch((unsigned)grid, threads, smem, P)) return false;
   } else {
-    CFB_LAUNCH(engine_c2c_kernel, (unsigned)grid, CFB_ENGINE_THREADS, smem, current_stream(), P);
+    CFB_LAUNCH(engine_c2c_kernel, (unsigned)grid, threads, smem, current_stream(), P);
   }
   count_launch();
   return cuda_ok(cudaGetLastError(), "engine kernel launch");
