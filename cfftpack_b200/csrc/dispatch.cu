@@ -154,6 +154,10 @@ static bool launch_engine(EngineParams &P) {
     while (p2 * 2 <= T) p2 *= 2;
     T = p2;
   }
+  {
+    static const int force_T = getenv("CFB200_ENGINE_T") ? atoi(getenv("CFB200_ENGINE_T")) : 0;  // experiments
+    if (force_T > 0 && (size_t)force_T * per + fixed <= SMEM_MAX) T = force_T;
+  }
   if (T > units) T = units;
   if (real && T > 1) {  // keep the power of two after clamping to the batch
     long long p2 = 1;
