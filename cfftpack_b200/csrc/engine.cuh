@@ -32,9 +32,12 @@ __device__ __forceinline__ int fast_div(int n, int d, unsigned mag) { return d =
 /* padded position of element e inside a shared-memory row: one extra slot every 2^ps elements (ps = 31: none).
  * With ps = log2 of the first radix the scattered stores of the first pass are bank-conflict free. */
 __device__ __forceinline__ int padx(int e, int ps) { return e + (e >> ps); }
+/* compile-time switch: rows without padding skip the shift/add altogether */
+template <bool PAD>
+__device__ __forceinline__ int padq(int e, int ps) { return PAD ? e + (e >> ps) : e; }
 
 /* one radix-R pass over T sequences: src, dst are [T][ldz] complex arrays in shared memory       */
-template <int R, int DIR>
+template <int R, int DIR, bool PAD>
 __device__ __forceinline__ void pass_fixed(const cpx *__restrict__ src, cpx *__restrict__ dst, int T, int ldz, int M,
                                            const PassDesc &pd, const cpx *__restrict__ tw, int tid, int nthr, int ps) {
   const int nb = M / R;  // butterflies per sequence
@@ -47,24 +50,24 @@ __device__ __forceinline__ void pass_fixed(const cpx *__restrict__ src, cpx *__r
     cpx a[R];
     const cpx *sp = src + t * ldz;
 #pragma unroll
-    for (int j = 0; j < R; ++j) a[j] = sp[padx(b + j * nb, ps)];
+    for (int j = 0; j < R; ++j) a[j] = sp[padq<PAD>(b + j * nb, ps)];
     DftRt<R, DIR>::run(a, tw + pd.rtoff);
     cpx *dp = dst + t * ldz;
     const int o0 = q + s * R * p;
-    dp[padx(o0, ps)] = a[0];
+    dp[padq<PAD>(o0, ps)] = a[0];
     if (m > 1) {
 #pragma unroll
-      for (int k = 1; k < R; ++k) dp[padx(o0 + k * s, ps)] = ctw<DIR>(a[k], twp[(k - 1) * m + p]);
+      for (int k = 1; k < R; ++k) dp[padq<PAD>(o0 + k * s, ps)] = ctw<DIR>(a[k], twp[(k - 1) * m + p]);
     } else {
 #pragma unroll
-      for (int k = 1; k < R; ++k) dp[padx(o0 + k * s, ps)] = a[k];
+      for (int k = 1; k < R; ++k) dp[padq<PAD>(o0 + k * s, ps)] = a[k];
     }
   }
 }
 
 /* generic odd radix r (the reference's c1fgkf_/c1fgkb_, fftpack.c:1650/:1410): each thread produces the
  * output pair (k, r-k) of one butterfly from the symmetric sums, O(r) work per output */
-template <int DIR>
+template <int DIR, bool PAD>
 __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *__restrict__ dst, int T, int ldz, int M,
                                              const PassDesc &pd, const cpx *__restrict__ tw, int tid, int nthr, int ps) {
   const int r = pd.radix, nb = M / r, s = pd.s, m = pd.m, half = (r + 1) / 2;
@@ -79,11 +82,11 @@ __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *_
     const cpx *sp = src + t * ldz;
     cpx *dp = dst + t * ldz;
     const int o0 = q + s * r * p;
-    cpx a0 = sp[padx(b, ps)];
+    cpx a0 = sp[padq<PAD>(b, ps)];
     if (k == 0) {
       cpx acc = a0;
-      for (int j = 1; j < r; ++j) acc = cadd(acc, sp[padx(b + j * nb, ps)]);
-      dp[padx(o0, ps)] = acc;
+      for (int j = 1; j < r; ++j) acc = cadd(acc, sp[padq<PAD>(b + j * nb, ps)]);
+      dp[padq<PAD>(o0, ps)] = acc;
     } else {
       // X_k = a0 + sum_{j=1}^{half-1} [ c_jk (a_j + a_{r-j}) + DIR*i * s_jk (a_j - a_{r-j}) ],  X_{r-k}: minus sign
       double ar = a0.x, ai = a0.y, br = 0.0, bi = 0.0;
@@ -92,7 +95,7 @@ __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *_
         jk += k;
         if (jk >= r) jk -= r;
         cpx w = rt[jk];  // (cos, -sin)(2 pi jk / r)
-        cpx u = sp[padx(b + j * nb, ps)], v = sp[padx(b + (r - j) * nb, ps)];
+        cpx u = sp[padq<PAD>(b + j * nb, ps)], v = sp[padq<PAD>(b + (r - j) * nb, ps)];
         double pr = u.x + v.x, pi = u.y + v.y, mr = u.x - v.x, mi = u.y - v.y;
         ar = fma(w.x, pr, ar);
         ai = fma(w.x, pi, ai);
@@ -112,37 +115,44 @@ __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *_
         xk = ctw<DIR>(xk, twp[(k - 1) * m + p]);
         xc = ctw<DIR>(xc, twp[(r - k - 1) * m + p]);
       }
-      dp[padx(o0 + k * s, ps)] = xk;
-      dp[padx(o0 + (r - k) * s, ps)] = xc;
+      dp[padq<PAD>(o0 + k * s, ps)] = xk;
+      dp[padq<PAD>(o0 + (r - k) * s, ps)] = xc;
     }
   }
 }
 
-template <int DIR>
-__device__ __forceinline__ void run_passes(cpx *&cur, cpx *&oth, const EngineParams &P, const cpx *__restrict__ tw,
-                                           int tid, int nthr) {
+template <int DIR, bool PAD>
+__device__ __forceinline__ void run_passes_impl(cpx *&cur, cpx *&oth, const EngineParams &P, const cpx *__restrict__ tw,
+                                                int tid, int nthr) {
   const int ps = P.padshift;
   for (int ip = 0; ip < P.nf; ++ip) {
     const PassDesc &pd = P.pass[ip];
     switch (pd.radix) {
-      case 2: pass_fixed<2, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      case 3: pass_fixed<3, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      case 4: pass_fixed<4, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      case 5: pass_fixed<5, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      case 6: pass_fixed<6, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      case 7: pass_fixed<7, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      case 8: pass_fixed<8, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      case 9: pass_fixed<9, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      case 10: pass_fixed<10, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      case 11: pass_fixed<11, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      case 13: pass_fixed<13, DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
-      default: pass_generic<DIR>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 2: pass_fixed<2, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 3: pass_fixed<3, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 4: pass_fixed<4, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 5: pass_fixed<5, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 6: pass_fixed<6, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 7: pass_fixed<7, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 8: pass_fixed<8, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 9: pass_fixed<9, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 10: pass_fixed<10, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 11: pass_fixed<11, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      case 13: pass_fixed<13, DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
+      default: pass_generic<DIR, PAD>(cur, oth, P.T, P.ldz, P.M, pd, tw, tid, nthr, ps); break;
     }
     __syncthreads();
     cpx *t = cur;
     cur = oth;
     oth = t;
   }
+}
+/* PAD = false is the only variant the real-family kernel needs (its rows are never padded) */
+template <int DIR, bool ALLOW_PAD = true>
+__device__ __forceinline__ void run_passes(cpx *&cur, cpx *&oth, const EngineParams &P, const cpx *__restrict__ tw,
+                                           int tid, int nthr) {
+  if (ALLOW_PAD && P.padshift != 31) run_passes_impl<DIR, true>(cur, oth, P, tw, tid, nthr);
+  else run_passes_impl<DIR, false>(cur, oth, P, tw, tid, nthr);
 }
 
 __device__ __forceinline__ long long batch_off(const Addr &a, long long g) {
@@ -601,7 +611,7 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
       __syncthreads();
       cur = A;
       oth = zB;
-      run_passes<-1>(cur, oth, P, tw, tid, nthr);
+      run_passes<-1, false>(cur, oth, P, tw, tid, nthr);
       /* split: cur -> half-complex rows in oth */
       double *hs = (double *)oth;
       const int nfq = M / 2 + 1;
@@ -621,7 +631,7 @@ __global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const Eng
       __syncthreads();
       cur = zB;
       oth = A;
-      run_passes<1>(cur, oth, P, tw, tid, nthr);
+      run_passes<1, false>(cur, oth, P, tw, tid, nthr);
       /* extract: re/im of cur -> real rows in oth */
       double *us = (double *)oth;
       for (int t = 0; t < T; ++t)
