@@ -16,6 +16,7 @@
 #include "internal.h"
 #include "plan.h"
 #include "pow2.cuh"
+#include "radix10.cuh"
 
 namespace cfb {
 
@@ -314,6 +315,7 @@ bool run_c2c_scaled(int n, long long lot, long long inc, long long jump, int dir
   if (n <= 1 || lot <= 0) return true;
   const int aligned = (((uintptr_t)c) & 15) == 0;
   if (pow2_c2c_supported(n, inc, jump, aligned)) return pow2_c2c_launch(n, lot, jump, dir, (cpx *)c, scale);
+  if (r10_supported(n) && inc == 1 && jump >= n && aligned) return r10_c2c_launch(n, lot, jump, dir, (cpx *)c, scale);
   EngineParams P;
   memset(&P, 0, sizeof(P));
   P.kind = K_C2C;
@@ -531,6 +533,8 @@ bool run_real(int kind, int n, long long lot, long long inc, long long jump, int
   }
   if (kind == K_RFFT && pow2_r2c_supported(n, inc, jump, (((uintptr_t)x) & 15) == 0))
     return pow2_r2c_launch(n, lot, jump, dir, x);
+  if (kind == K_RFFT && r10_supported(n) && inc == 1 && jump >= n && jump % 2 == 0 && (((uintptr_t)x) & 15) == 0)
+    return r10_r2c_launch(n, lot, jump, dir, x);
   const int M = kind == K_COST ? n - 1 : kind == K_SINT ? n + 1 : n;
   if (M >= long_real_threshold() || n >= long_real_threshold()) return run_real_long(kind, n, M, lot, inc, jump, dir, x);
   EngineParams P;

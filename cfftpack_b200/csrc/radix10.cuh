@@ -1,0 +1,283 @@
+/*
+ * radix10.cuh -- register-resident streaming kernels for N = 10^K (100, 1000): the radix-2/5 lengths of
+ * BASELINE config 4 ("N = 1000, radix 2.2.2.5.5.5").  Same design as the power-of-two stream kernels (pow2.cuh):
+ * persistent CTAs, TMA bulk loads one tile ahead, N/10 threads per sequence holding 10 points each, one in-register
+ * radix-10 DFT + twiddle + shared-memory exchange per stage (1000 = 10.10.10 -> two exchanges), real and imaginary
+ * parts exchanged in two rounds through one double-per-element tile.  Replaces for these lengths the passes
+ * c1f2kf_/c1f5kf_ + c1f4kf_ (cfftpack/fftpack.c:195, :1145, :752) of cfftmf_/cfftmb_ and, with the pair packing of
+ * pow2.cuh, the mradf2/mradf4/mradf5 passes (:8600, :8880, :9099) of rfftmf_/rfftmb_.
+ * Threads per sequence are padded to a multiple of 16/128 (idle threads only take part in the barriers).
+ */
+#ifndef CFB_RADIX10_CUH
+#define CFB_RADIX10_CUH
+#include "pow2.cuh"
+
+namespace cfb {
+
+/* 10-point DFT in registers: two 5-point DFTs (even / odd inputs) and a radix-2 level with the 10th roots */
+template <int DIR>
+__device__ __forceinline__ void dft10(cpx (&a)[10]) {
+  const double C36 = 0.80901699437494742410229341718282, S36 = 0.58778525229247312916870595463907;
+  const double C72 = 0.30901699437494742410229341718282, S72 = 0.95105651629515357211643933337938;
+  cpx e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], e4 = a[8];
+  cpx o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7], o4 = a[9];
+  dft5<DIR>(e0, e1, e2, e3, e4);
+  dft5<DIR>(o0, o1, o2, o3, o4);
+  // X[k] = E[k] + w10^k O[k], X[k+5] = E[k] - w10^k O[k];  forward w10^k = (cos 36k, -sin 36k)
+  o1 = ctw<DIR>(o1, make_double2(C36, -S36));
+  o2 = ctw<DIR>(o2, make_double2(C72, -S72));
+  o3 = ctw<DIR>(o3, make_double2(-C72, -S72));
+  o4 = ctw<DIR>(o4, make_double2(-C36, -S36));
+  a[0] = cadd(e0, o0);
+  a[5] = csub(e0, o0);
+  a[1] = cadd(e1, o1);
+  a[6] = csub(e1, o1);
+  a[2] = cadd(e2, o2);
+  a[7] = csub(e2, o2);
+  a[3] = cadd(e3, o3);
+  a[8] = csub(e3, o3);
+  a[4] = cadd(e4, o4);
+  a[9] = csub(e4, o4);
+}
+
+/* a[k] *= w^k, k = 1..9, from w1 = w and w4 = w^4 */
+template <int DIR>
+__device__ __forceinline__ void twiddle_powers10(cpx (&a)[10], cpx w1, cpx w4) {
+  cpx w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+  a[1] = ctw<DIR>(a[1], w1);
+  a[2] = ctw<DIR>(a[2], w2);
+  a[3] = ctw<DIR>(a[3], w3);
+  a[4] = ctw<DIR>(a[4], w4);
+  a[5] = ctw<DIR>(a[5], cmul(w4, w1));
+  a[6] = ctw<DIR>(a[6], cmul(w4, w2));
+  a[7] = ctw<DIR>(a[7], cmul(w4, w3));
+  cpx w8 = cmul(w4, w4);
+  a[8] = ctw<DIR>(a[8], w8);
+  a[9] = ctw<DIR>(a[9], cmul(w8, w1));
+}
+
+template <int K>
+struct R10Cfg {
+  static constexpr int P = 10;
+  static constexpr int N = (K == 2) ? 100 : 1000;
+  static constexpr int NT = N / P;                       // working threads per sequence
+  static constexpr int NTP = (NT <= 16) ? 16 : 128;      // threads reserved per sequence (padded)
+  static constexpr int THREADS = 256;
+  static constexpr int TPB = THREADS / NTP;              // sequences (pairs) per CTA
+  static constexpr int XT = N + 4 * (N / P);             // exchange row: 4 pad doubles per 10 (14-double pitch: rows stay
+                                                         // 16-byte aligned and the 16-byte stores of stage 0 conflict-free)
+  static constexpr int stage_s(int st) { return st == 0 ? 1 : st == 1 ? 10 : 100; }
+  static constexpr int stage_m(int st) { return N / (stage_s(st) * P); }
+  static constexpr int tws_offset(int st) {
+    int off = 0;
+    for (int i = 0; i < st; ++i) off += 2 * stage_m(i);
+    return off;
+  }
+  static constexpr int TWS_COUNT = tws_offset(K - 1);    // the last stage has no twiddles
+  static constexpr size_t LAND = (size_t)TPB * N * sizeof(cpx);
+  static constexpr size_t XCH = (size_t)TPB * XT * sizeof(double);
+  static constexpr size_t TWS = (size_t)(TWS_COUNT > 0 ? TWS_COUNT : 1) * sizeof(cpx);
+  static constexpr size_t BYTES = LAND + XCH + TWS + 16;
+  static __device__ __forceinline__ int xpad(int e) { return e + 4 * (e / P); }
+};
+
+/* all K stages; a[i] <-> element t + NT*i on entry and exit.  act = false: idle thread (barriers only) */
+template <class C, int K, int DIR>
+__device__ __forceinline__ void r10_core(cpx (&a)[10], double *__restrict__ xr, const int t, const bool act,
+                                         const cpx *__restrict__ tws) {
+  constexpr int P = 10, NT = C::NT;
+#pragma unroll
+  for (int st = 0; st < K; ++st) {
+    const int s = C::stage_s(st), m = C::stage_m(st);
+    dft10<DIR>(a);
+    if (st < K - 1) {
+      const int p = t / s, q = t % s;
+      const cpx *twp = tws + C::tws_offset(st) + (act ? p : 0);
+      twiddle_powers10<DIR>(a, twp[0], twp[m]);
+      const int base = q + s * P * p;
+      if (act) {
+        if (st == 0) {
+          double2 *row = (double2 *)(xr + C::xpad(base));
+#pragma unroll
+          for (int k = 0; k < P; k += 2) row[k / 2] = make_double2(a[k].x, a[k + 1].x);
+        } else {
+#pragma unroll
+          for (int k = 0; k < P; ++k) xr[C::xpad(base + s * k)] = a[k].x;
+        }
+      }
+      __syncthreads();
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) a[i].x = xr[C::xpad(t + NT * i)];
+      }
+      __syncthreads();
+      if (act) {
+        if (st == 0) {
+          double2 *row = (double2 *)(xr + C::xpad(base));
+#pragma unroll
+          for (int k = 0; k < P; k += 2) row[k / 2] = make_double2(a[k].y, a[k + 1].y);
+        } else {
+#pragma unroll
+          for (int k = 0; k < P; ++k) xr[C::xpad(base + s * k)] = a[k].y;
+        }
+      }
+      __syncthreads();
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) a[i].y = xr[C::xpad(t + NT * i)];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int K, int DIR>
+__global__ void __launch_bounds__(256, 2) r10_c2c_stream_kernel(cpx *__restrict__ c, long long lot, long long jump,
+                                                                const cpx *__restrict__ tw, double scale, long long ntiles) {
+  typedef R10Cfg<K> C;
+  CFB_DYN_SMEM(smem_raw);
+  constexpr int N = C::N, P = 10, NT = C::NT;
+  cpx *land = (cpx *)smem_raw;
+  double *xch = (double *)(smem_raw + C::LAND);
+  cpx *tws = (cpx *)(smem_raw + C::LAND + C::XCH);
+  uint64_t *bar = (uint64_t *)(smem_raw + C::LAND + C::XCH + C::TWS);
+  const int tid = threadIdx.x, tl = tid / C::NTP, t = tid % C::NTP;
+  const bool act = t < NT;
+  if (tid == 0) mbar_init(bar, 1);
+  for (int i = tid; i < C::TWS_COUNT; i += C::THREADS) tws[i] = __ldg(tw + i);
+  __syncthreads();
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, tile, N * 16, bar);
+  unsigned parity = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const long long g = tile * C::TPB + tl;
+    const bool live = act && g < lot;
+    cpx a[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) a[i] = act ? land[(size_t)tl * N + t + NT * i] : make_double2(0.0, 0.0);
+    __syncthreads();
+    const long long next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
+    r10_core<C, K, DIR>(a, xch + (size_t)tl * C::XT, t, act, tws);
+    if (live) {
+      cpx *x = c + g * jump + t;
+#pragma unroll
+      for (int i = 0; i < P; ++i) x[NT * i] = make_double2(a[i].x * scale, a[i].y * scale);
+    }
+  }
+}
+
+/* two real rows per complex transform (see pow2_r2c_stream_kernel); DIR = -1 rfftmf_, +1 rfftmb_ */
+template <int K, int DIR>
+__global__ void __launch_bounds__(256, 2) r10_r2c_stream_kernel(double *__restrict__ r, long long lot, long long jump,
+                                                                const cpx *__restrict__ tw, long long ntiles) {
+  typedef R10Cfg<K> C;
+  CFB_DYN_SMEM(smem_raw);
+  constexpr int N = C::N, P = 10, NT = C::NT;
+  double *land = (double *)smem_raw;  // [TPB][2][N]
+  double *xch = (double *)(smem_raw + C::LAND);
+  cpx *tws = (cpx *)(smem_raw + C::LAND + C::XCH);
+  uint64_t *bar = (uint64_t *)(smem_raw + C::LAND + C::XCH + C::TWS);
+  const int tid = threadIdx.x, tl = tid / C::NTP, t = tid % C::NTP;
+  const bool act = t < NT;
+  if (tid == 0) mbar_init(bar, 1);
+  for (int i = tid; i < C::TWS_COUNT; i += C::THREADS) tws[i] = __ldg(tw + i);
+  __syncthreads();
+  constexpr int ROWS = 2 * C::TPB;
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, tile, N * 8, bar);
+  unsigned parity = 0;
+  const double *la = land + (size_t)(2 * tl) * N, *lb = la + N;
+  double *xq = xch + (size_t)tl * C::XT;
+  const int lane = tid & 31;
+  for (; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const long long ga = 2 * (tile * C::TPB + tl), gb = ga + 1;
+    const bool va = act && ga < lot, vb = act && gb < lot;
+    double *xa = r + (va ? ga : 0) * jump, *xb = r + (vb ? gb : 0) * jump;
+    cpx a[P];
+    if (DIR < 0) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) a[i] = make_double2(va ? la[t + NT * i] : 0.0, vb ? lb[t + NT * i] : 0.0);
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        const int e = t + NT * i;
+        a[i] = make_double2(0.0, 0.0);
+        if (act) {
+          if (e == 0) a[i] = make_double2(va ? la[0] : 0.0, vb ? lb[0] : 0.0);
+          else if (e == N / 2) a[i] = make_double2(va ? la[N - 1] : 0.0, vb ? lb[N - 1] : 0.0);
+          else {
+            const int f = e < N / 2 ? e : N - e;
+            double a1 = va ? 0.5 * la[2 * f - 1] : 0.0, a2 = va ? 0.5 * la[2 * f] : 0.0;
+            double b1 = vb ? 0.5 * lb[2 * f - 1] : 0.0, b2 = vb ? 0.5 * lb[2 * f] : 0.0;
+            a[i] = e < N / 2 ? make_double2(a1 + b2, b1 - a2) : make_double2(a1 - b2, b1 + a2);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const long long next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
+    r10_core<C, K, DIR>(a, xq, t, act, tws);
+    if (DIR < 0) {
+      cpx *zq = (cpx *)xq;  // N/2 complex slots for the upper half of the spectrum
+      if (act) {
+#pragma unroll
+        for (int i = P / 2; i < P; ++i) zq[t + NT * (i - P / 2)] = a[i];
+      }
+      __syncthreads();
+      const double sc = 1.0 / (double)N;
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        const int f = t + NT * i;
+        cpx u = a[i], v = act ? zq[f == 0 ? 0 : N / 2 - f] : make_double2(0.0, 0.0);
+        double Aa, Ba, Ab, Bb;
+        if (f == 0) {
+          Aa = 0.0;
+          Ab = 0.0;
+          Ba = u.x * sc;
+          Bb = u.y * sc;
+        } else {
+          Aa = (u.x + v.x) * sc;
+          Ba = (v.y - u.y) * sc;
+          Ab = (u.y + v.y) * sc;
+          Bb = (u.x - v.x) * sc;
+        }
+        const double Aa_n = __shfl_down_sync(0xffffffffu, Aa, 1), Ab_n = __shfl_down_sync(0xffffffffu, Ab, 1);
+        if (lane < 31 && t != NT - 1) {
+          if (va) *(double2 *)(xa + 2 * f) = make_double2(Ba, Aa_n);
+          if (vb) *(double2 *)(xb + 2 * f) = make_double2(Bb, Ab_n);
+        } else {
+          if (va) xa[2 * f] = Ba;
+          if (vb) xb[2 * f] = Bb;
+        }
+        if ((lane == 0 || t == 0) && f != 0) {
+          if (va) xa[2 * f - 1] = Aa;
+          if (vb) xb[2 * f - 1] = Ab;
+        }
+        if (f == 0) {
+          if (va) xa[N - 1] = v.x * sc;
+          if (vb) xb[N - 1] = v.y * sc;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        if (va) xa[t + NT * i] = a[i].x;
+        if (vb) xb[t + NT * i] = a[i].y;
+      }
+    }
+  }
+}
+
+/* host side (radix10.cu) */
+bool r10_supported(int n);
+bool r10_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c, double scale);
+bool r10_r2c_launch(int n, long long lot, long long jump, int dir, double *r);
+
+}  // namespace cfb
+#endif
