@@ -535,6 +535,11 @@ bool run_real(int kind, int n, long long lot, long long inc, long long jump, int
     return pow2_r2c_launch(n, lot, jump, dir, x);
   if (kind == K_RFFT && r10_supported(n) && inc == 1 && jump >= n && jump % 2 == 0 && (((uintptr_t)x) & 15) == 0)
     return r10_r2c_launch(n, lot, jump, dir, x);
+  if (kind == K_COSQ && r10_supported(n) && inc == 1 && jump >= n && jump % 2 == 0 && (((uintptr_t)x) & 15) == 0) {
+    const TrigPlan *tp = get_trig_plan(K_COSQ, n);
+    if (!tp) return false;
+    return r10_cosq_launch(n, lot, jump, dir, x, tp->d_trig);
+  }
   const int M = kind == K_COST ? n - 1 : kind == K_SINT ? n + 1 : n;
   if (M >= long_real_threshold() || n >= long_real_threshold()) return run_real_long(kind, n, M, lot, inc, jump, dir, x);
   EngineParams P;

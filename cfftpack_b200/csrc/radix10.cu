@@ -78,18 +78,19 @@ bool launch_c2c(long long lot, long long jump, cpx *c, double scale) {
   return cuda_ok(cudaGetLastError(), "r10_c2c_stream_kernel launch");
 }
 
-template <int K, int DIR>
-bool launch_r2c(long long lot, long long jump, double *r) {
+template <int K, int KIND, int DIR>
+bool launch_r2c(long long lot, long long jump, double *r, const double *trig) {
   typedef R10Cfg<K> C;
   const cpx *tw = r10_table<K>();
   if (!tw) return false;
   static std::once_flag once;
   static bool ok = true;
-  auto kern = r10_r2c_stream_kernel<K, DIR>;
-  if (!attr_once(kern, C::BYTES, once, ok)) return false;
+  auto kern = r10_r2c_stream_kernel<K, KIND, DIR>;
+  const size_t smem = KIND == K_COSQ ? C::BYTES_TRIG : C::BYTES;
+  if (!attr_once(kern, smem, once, ok)) return false;
   const long long pairs = (lot + 1) / 2;
   const long long ntiles = (pairs + C::TPB - 1) / C::TPB;
-  CFB_LAUNCH(kern, (unsigned)grid_for<K>(ntiles), C::THREADS, C::BYTES, current_stream(), r, lot, jump, tw, ntiles);
+  CFB_LAUNCH(kern, (unsigned)grid_for<K>(ntiles), C::THREADS, smem, current_stream(), r, lot, jump, tw, trig, ntiles);
   count_launch();
   return cuda_ok(cudaGetLastError(), "r10_r2c_stream_kernel launch");
 }
@@ -104,9 +105,15 @@ bool r10_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c, doubl
   return false;
 }
 bool r10_r2c_launch(int n, long long lot, long long jump, int dir, double *r) {
-  if (n == 100) return dir < 0 ? launch_r2c<2, -1>(lot, jump, r) : launch_r2c<2, 1>(lot, jump, r);
-  if (n == 1000) return dir < 0 ? launch_r2c<3, -1>(lot, jump, r) : launch_r2c<3, 1>(lot, jump, r);
+  if (n == 100) return dir < 0 ? launch_r2c<2, K_RFFT, -1>(lot, jump, r, nullptr) : launch_r2c<2, K_RFFT, 1>(lot, jump, r, nullptr);
+  if (n == 1000) return dir < 0 ? launch_r2c<3, K_RFFT, -1>(lot, jump, r, nullptr) : launch_r2c<3, K_RFFT, 1>(lot, jump, r, nullptr);
   set_error("r10_r2c_launch: unsupported length %d", n);
+  return false;
+}
+bool r10_cosq_launch(int n, long long lot, long long jump, int dir, double *x, const double *trig) {
+  if (n == 100) return dir < 0 ? launch_r2c<2, K_COSQ, -1>(lot, jump, x, trig) : launch_r2c<2, K_COSQ, 1>(lot, jump, x, trig);
+  if (n == 1000) return dir < 0 ? launch_r2c<3, K_COSQ, -1>(lot, jump, x, trig) : launch_r2c<3, K_COSQ, 1>(lot, jump, x, trig);
+  set_error("r10_cosq_launch: unsupported length %d", n);
   return false;
 }
 

@@ -78,6 +78,7 @@ struct R10Cfg {
   static constexpr size_t XCH = (size_t)TPB * XT * sizeof(double);
   static constexpr size_t TWS = (size_t)(TWS_COUNT > 0 ? TWS_COUNT : 1) * sizeof(cpx);
   static constexpr size_t BYTES = LAND + XCH + TWS + 16;
+  static constexpr size_t BYTES_TRIG = BYTES + (size_t)N * sizeof(double);  // + cosq table
   static __device__ __forceinline__ int xpad(int e) { return e + 4 * (e / P); }
 };
 
@@ -169,10 +170,14 @@ __global__ void __launch_bounds__(256, 2) r10_c2c_stream_kernel(cpx *__restrict_
   }
 }
 
-/* two real rows per complex transform (see pow2_r2c_stream_kernel); DIR = -1 rfftmf_, +1 rfftmb_ */
-template <int K, int DIR>
+/* two real rows per complex transform (see pow2_r2c_stream_kernel).  KIND = K_RFFT: rfftmf_ / rfftmb_;
+ * KIND = K_COSQ: cosqmf_ / cosqmb_ with the fold and the pairwise post-processing of cosqf1_/cosqb1_
+ * (fftpack.c:5693-5738, :5604-5652) fused into the register load and the store (trig[i] = cos((i+1) pi / 2n) in
+ * shared memory).  DIR = -1 forward, +1 backward (user-level direction). */
+template <int K, int KIND, int DIR>
 __global__ void __launch_bounds__(256, 2) r10_r2c_stream_kernel(double *__restrict__ r, long long lot, long long jump,
-                                                                const cpx *__restrict__ tw, long long ntiles) {
+                                                                const cpx *__restrict__ tw, const double *__restrict__ trig_g,
+                                                                long long ntiles) {
   typedef R10Cfg<K> C;
   CFB_DYN_SMEM(smem_raw);
   constexpr int N = C::N, P = 10, NT = C::NT;
@@ -180,10 +185,13 @@ __global__ void __launch_bounds__(256, 2) r10_r2c_stream_kernel(double *__restri
   double *xch = (double *)(smem_raw + C::LAND);
   cpx *tws = (cpx *)(smem_raw + C::LAND + C::XCH);
   uint64_t *bar = (uint64_t *)(smem_raw + C::LAND + C::XCH + C::TWS);
+  double *W = (double *)(bar + 2);  // cosq: trig table, N doubles
   const int tid = threadIdx.x, tl = tid / C::NTP, t = tid % C::NTP;
   const bool act = t < NT;
   if (tid == 0) mbar_init(bar, 1);
   for (int i = tid; i < C::TWS_COUNT; i += C::THREADS) tws[i] = __ldg(tw + i);
+  if (KIND == K_COSQ)
+    for (int i = tid; i < N; i += C::THREADS) W[i] = __ldg(trig_g + i);
   __syncthreads();
   constexpr int ROWS = 2 * C::TPB;
   long long tile = blockIdx.x;
@@ -200,20 +208,55 @@ __global__ void __launch_bounds__(256, 2) r10_r2c_stream_kernel(double *__restri
     double *xa = r + (va ? ga : 0) * jump, *xb = r + (vb ? gb : 0) * jump;
     cpx a[P];
     if (DIR < 0) {
+      if (KIND == K_COSQ) {
+        // cosqf1_ fold: u[0] = x[0]; u[j] = W[j-1] (x[j]-x[n-j]) + W[n-j-1] (x[j]+x[n-j]);
+        //               u[n-j] = W[j-1] (x[j]+x[n-j]) - W[n-j-1] (x[j]-x[n-j]);  u[n/2] = W[n/2-1] 2 x[n/2]
 #pragma unroll
-      for (int i = 0; i < P; ++i) a[i] = make_double2(va ? la[t + NT * i] : 0.0, vb ? lb[t + NT * i] : 0.0);
+        for (int i = 0; i < P; ++i) {
+          const int e = t + NT * i;
+          a[i] = make_double2(0.0, 0.0);
+          if (act) {
+            if (e == 0) a[i] = make_double2(va ? la[0] : 0.0, vb ? lb[0] : 0.0);
+            else if (e == N / 2) {
+              const double w = 2.0 * W[N / 2 - 1];
+              a[i] = make_double2(va ? w * la[e] : 0.0, vb ? w * lb[e] : 0.0);
+            } else {
+              const int j = e < N / 2 ? e : N - e, jc = N - j;
+              const double wj = W[j - 1], wc = W[jc - 1];
+              const double sa = va ? la[j] + la[jc] : 0.0, da = va ? la[j] - la[jc] : 0.0;
+              const double sb = vb ? lb[j] + lb[jc] : 0.0, db = vb ? lb[j] - lb[jc] : 0.0;
+              a[i] = e < N / 2 ? make_double2(fma(wj, da, wc * sa), fma(wj, db, wc * sb))
+                               : make_double2(fma(wj, sa, -(wc * da)), fma(wj, sb, -(wc * db)));
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) a[i] = make_double2(va ? la[t + NT * i] : 0.0, vb ? lb[t + NT * i] : 0.0);
+      }
     } else {
+      // half-complex row h -> spectrum Z (rfftb1_ convention).  cosqb1_ first forms h from x:
+      //   h[0] = x[0]/2, h[2f-1] = (x[2f-1]+x[2f])/2, h[2f] = (x[2f-1]-x[2f])/2, h[n-1] = x[n-1]/2
 #pragma unroll
       for (int i = 0; i < P; ++i) {
         const int e = t + NT * i;
         a[i] = make_double2(0.0, 0.0);
         if (act) {
-          if (e == 0) a[i] = make_double2(va ? la[0] : 0.0, vb ? lb[0] : 0.0);
-          else if (e == N / 2) a[i] = make_double2(va ? la[N - 1] : 0.0, vb ? lb[N - 1] : 0.0);
+          const double edge = (KIND == K_COSQ) ? 0.5 : 1.0;
+          if (e == 0) a[i] = make_double2(va ? edge * la[0] : 0.0, vb ? edge * lb[0] : 0.0);
+          else if (e == N / 2) a[i] = make_double2(va ? edge * la[N - 1] : 0.0, vb ? edge * lb[N - 1] : 0.0);
           else {
             const int f = e < N / 2 ? e : N - e;
-            double a1 = va ? 0.5 * la[2 * f - 1] : 0.0, a2 = va ? 0.5 * la[2 * f] : 0.0;
-            double b1 = vb ? 0.5 * lb[2 * f - 1] : 0.0, b2 = vb ? 0.5 * lb[2 * f] : 0.0;
+            double h1a = va ? la[2 * f - 1] : 0.0, h2a = va ? la[2 * f] : 0.0;
+            double h1b = vb ? lb[2 * f - 1] : 0.0, h2b = vb ? lb[2 * f] : 0.0;
+            if (KIND == K_COSQ) {
+              const double s1 = 0.5 * (h1a + h2a), d1 = 0.5 * (h1a - h2a), s2 = 0.5 * (h1b + h2b), d2 = 0.5 * (h1b - h2b);
+              h1a = s1;
+              h2a = d1;
+              h1b = s2;
+              h2b = d2;
+            }
+            const double a1 = 0.5 * h1a, a2 = 0.5 * h2a, b1 = 0.5 * h1b, b2 = 0.5 * h2b;
             a[i] = e < N / 2 ? make_double2(a1 + b2, b1 - a2) : make_double2(a1 - b2, b1 + a2);
           }
         }
@@ -246,6 +289,13 @@ __global__ void __launch_bounds__(256, 2) r10_r2c_stream_kernel(double *__restri
           Ba = (v.y - u.y) * sc;
           Ab = (u.y + v.y) * sc;
           Bb = (u.x - v.x) * sc;
+          if (KIND == K_COSQ) {  // cosqf1_ post: y[2f-1] = (A_f + B_f)/2, y[2f] = (A_f - B_f)/2
+            const double s1 = 0.5 * (Aa + Ba), d1 = 0.5 * (Aa - Ba), s2 = 0.5 * (Ab + Bb), d2 = 0.5 * (Ab - Bb);
+            Aa = s1;
+            Ba = d1;
+            Ab = s2;
+            Bb = d2;
+          }
         }
         const double Aa_n = __shfl_down_sync(0xffffffffu, Aa, 1), Ab_n = __shfl_down_sync(0xffffffffu, Ab, 1);
         if (lane < 31 && t != NT - 1) {
@@ -264,6 +314,45 @@ __global__ void __launch_bounds__(256, 2) r10_r2c_stream_kernel(double *__restri
           if (vb) xb[N - 1] = v.y * sc;
         }
       }
+    } else if (KIND == K_COSQ) {
+      // cosqb1_ post: y[0] = 2 u[0]; y[j] = p + q, y[n-j] = p - q with p = W[j-1] u[n-j] + W[n-j-1] u[j],
+      // q = W[j-1] u[j] - W[n-j-1] u[n-j]; y[n/2] = W[n/2-1] 2 u[n/2].  u[n-j] of the upper half goes through zq.
+      cpx *zq = (cpx *)xq;
+      if (act) {
+#pragma unroll
+        for (int i = P / 2; i < P; ++i) zq[t + NT * (i - P / 2)] = a[i];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        const int j = t + NT * i;
+        if (!act) continue;
+        if (j == 0) {
+          const cpx mid = zq[0];
+          const double w = 2.0 * W[N / 2 - 1];
+          if (va) {
+            xa[0] = a[0].x + a[0].x;
+            xa[N / 2] = w * mid.x;
+          }
+          if (vb) {
+            xb[0] = a[0].y + a[0].y;
+            xb[N / 2] = w * mid.y;
+          }
+        } else {
+          const cpx uj = a[i], uc = zq[N / 2 - j];
+          const double wj = W[j - 1], wc = W[N - j - 1];
+          const double pa = fma(wj, uc.x, wc * uj.x), qa = fma(wj, uj.x, -(wc * uc.x));
+          const double pb = fma(wj, uc.y, wc * uj.y), qb = fma(wj, uj.y, -(wc * uc.y));
+          if (va) {
+            xa[j] = pa + qa;
+            xa[N - j] = pa - qa;
+          }
+          if (vb) {
+            xb[j] = pb + qb;
+            xb[N - j] = pb - qb;
+          }
+        }
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < P; ++i) {
@@ -278,6 +367,7 @@ __global__ void __launch_bounds__(256, 2) r10_r2c_stream_kernel(double *__restri
 bool r10_supported(int n);
 bool r10_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c, double scale);
 bool r10_r2c_launch(int n, long long lot, long long jump, int dir, double *r);
+bool r10_cosq_launch(int n, long long lot, long long jump, int dir, double *x, const double *trig);
 
 }  // namespace cfb
 #endif
