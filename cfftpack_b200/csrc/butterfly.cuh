@@ -247,6 +247,23 @@ __device__ __forceinline__ void dft_comp(cpx (&a)[A * B], const cpx *__restrict_
   }
 }
 
+/* ---- warp helpers (one warp works on one real sequence in the pre/post phases) ---- */
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+/* exclusive prefix over the lanes of a warp */
+__device__ __forceinline__ double warp_excl_scan(double v, int lane) {
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  return inc - v;
+}
+
 /* uniform entry point for the engine: radices that need the table of R-th roots take it from rt */
 template <int R, int DIR>
 struct DftRt {

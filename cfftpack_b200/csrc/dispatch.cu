@@ -540,6 +540,15 @@ bool run_real(int kind, int n, long long lot, long long inc, long long jump, int
     if (!tp) return false;
     return r10_cosq_launch(n, lot, jump, dir, x, tp->d_trig);
   }
+  if (kind == K_COST && n == 1001 && inc == 1 && jump == n && lot >= 2 && (((uintptr_t)x) & 15) == 0) {
+    // radix-10 register kernel on the even part of the batch; a last odd row goes through the general engine
+    const TrigPlan *tp = get_trig_plan(K_COST, n);
+    if (!tp) return false;
+    if (!r10_cost_launch(lot / 2, dir, x, tp->d_trig)) return false;
+    if (lot % 2 == 0) return true;
+    x += (lot - 1) * jump;
+    lot = 1;
+  }
   const int M = kind == K_COST ? n - 1 : kind == K_SINT ? n + 1 : n;
   if (M >= long_real_threshold() || n >= long_real_threshold()) return run_real_long(kind, n, M, lot, inc, jump, dir, x);
   EngineParams P;

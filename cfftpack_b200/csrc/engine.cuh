@@ -161,23 +161,6 @@ __device__ __forceinline__ long long batch_off(const Addr &a, long long g) {
   return hi * a.jump_hi + lo * a.jump_lo;
 }
 
-/* ---- warp helpers (one warp works on one real sequence in the pre/post phases) ---- */
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-/* exclusive prefix over the lanes of a warp */
-__device__ __forceinline__ double warp_excl_scan(double v, int lane) {
-  double inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    double u = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += u;
-  }
-  return inc - v;
-}
-
 /* ------------------------------------------------------------------------------------------ */
 /* forward real core, output side: Z = FFT(x_a + i x_b) (unscaled) -> FFTPACK half-complex rows ha, hb
  * scaled like rfftf1_ (fftpack.c:13818-13853): h[0]=X0/M, h[2f-1]=2Re X_f/M, h[2f]=-2Im X_f/M, h[M-1]=X_{M/2}/M */

@@ -96,6 +96,30 @@ bool launch_r2c(long long lot, long long jump, double *r, const double *trig) {
 }
 }  // namespace
 
+bool r10_cost_launch(long long npairs, int dir, double *x, const double *trig) {
+  typedef R10Cfg<3> C;
+  const cpx *tw = r10_table<3>();
+  if (!tw) return false;
+  static std::once_flag once_f, once_b;
+  static bool ok_f = true, ok_b = true;
+  const long long ntiles = (npairs + C::TPB - 1) / C::TPB;
+  long long per_sm = (long long)((SMEM_LIMIT + 1024) / (R10Cost::BYTES + 1024));
+  if (per_sm > 2) per_sm = 2;
+  long long grid = per_sm * sm_count();
+  if (grid > ntiles) grid = ntiles;
+  if (dir < 0) {
+    auto kern = r10_cost_stream_kernel<-1>;
+    if (!attr_once(kern, R10Cost::BYTES, once_f, ok_f)) return false;
+    CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, R10Cost::BYTES, current_stream(), x, npairs, tw, trig, ntiles);
+  } else {
+    auto kern = r10_cost_stream_kernel<1>;
+    if (!attr_once(kern, R10Cost::BYTES, once_b, ok_b)) return false;
+    CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, R10Cost::BYTES, current_stream(), x, npairs, tw, trig, ntiles);
+  }
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "r10_cost_stream_kernel launch");
+}
+
 bool r10_supported(int n) { return n == 100 || n == 1000; }
 
 bool r10_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c, double scale) {

@@ -363,11 +363,203 @@ __global__ void __launch_bounds__(256, 2) r10_r2c_stream_kernel(double *__restri
   }
 }
 
+/* DCT-I of length n = N + 1 = 1001 (costmf_ / costmb_, fftpack.c:6485, :6419 -> mcstf1_ :7150): the real transform
+ * underneath has length N = 1000.  Rows are contiguous (jump = n, odd), so a PAIR of rows is one 16-byte aligned run
+ * of 2n doubles -> one bulk copy per pair.  The pre-fold (:6355-6377) happens on the way from the landing buffer to
+ * the registers; dsum is a block reduction; the serial post recurrence (:6386-6400) is a two-level scan over the
+ * threads of the sequence.  Both directions use the forward real transform, like the reference. */
+struct R10Cost {
+  typedef R10Cfg<3> C;
+  static constexpr int N = 1000, n = 1001, NT = 100, NW = 4;  // NW warps per sequence
+  static constexpr size_t LAND = (size_t)C::TPB * 2 * n * sizeof(double);  // 32032 B (multiple of 16)
+  static constexpr size_t OFF_XCH = LAND;
+  static constexpr size_t OFF_TWS = OFF_XCH + C::XCH;
+  static constexpr size_t OFF_BAR = OFF_TWS + C::TWS;
+  static constexpr size_t OFF_TRIG = OFF_BAR + 16;                          // S[500], C[500]
+  static constexpr size_t OFF_RED = OFF_TRIG + (size_t)N * sizeof(double);  // per sequence: dsum partials [2][NW] + scan totals [2][5][NW]
+  static constexpr int RED_PER_SEQ = 2 * NW + 2 * 5 * NW;
+  static constexpr size_t BYTES = OFF_RED + (size_t)C::TPB * RED_PER_SEQ * sizeof(double) + 16;
+};
+
+template <int DIR>
+__global__ void __launch_bounds__(256, 2) r10_cost_stream_kernel(double *__restrict__ r, long long npairs,
+                                                                 const cpx *__restrict__ tw, const double *__restrict__ trig_g,
+                                                                 long long ntiles) {
+  typedef R10Cfg<3> C;
+  typedef R10Cost R;
+  CFB_DYN_SMEM(smem_raw);
+  constexpr int N = R::N, n = R::n, P = 10, NT = R::NT, NW = R::NW;
+  double *land = (double *)smem_raw;
+  double *xch = (double *)(smem_raw + R::OFF_XCH);
+  cpx *tws = (cpx *)(smem_raw + R::OFF_TWS);
+  uint64_t *bar = (uint64_t *)(smem_raw + R::OFF_BAR);
+  double *Ssm = (double *)(smem_raw + R::OFF_TRIG), *Csm = Ssm + N / 2;
+  double *red = (double *)(smem_raw + R::OFF_RED);
+  const int tid = threadIdx.x, tl = tid / C::NTP, t = tid % C::NTP, lane = tid & 31, w = t >> 5;
+  const bool act = t < NT;
+  if (tid == 0) mbar_init(bar, 1);
+  for (int i = tid; i < C::TWS_COUNT; i += C::THREADS) tws[i] = __ldg(tw + i);
+  for (int i = tid; i < N / 2; i += C::THREADS) {
+    Ssm[i] = __ldg(trig_g + i);       // 2 sin(i pi / N)
+    Csm[i] = __ldg(trig_g + N + i);   // 2 cos(i pi / N)
+  }
+  __syncthreads();
+  auto issue = [&](long long tile) {  // thread 0: one bulk copy for the live pairs of the tile (contiguous)
+    const long long p0 = tile * C::TPB;
+    const int live = (int)((npairs - p0) < C::TPB ? (npairs - p0) : C::TPB);
+    const unsigned bytes = (unsigned)live * 2 * n * 8;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(land, r + p0 * 2 * n, bytes, bar);
+  };
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) issue(tile);
+  unsigned parity = 0;
+  const double *la = land + (size_t)tl * 2 * n, *lb = la + n;
+  double *xq = xch + (size_t)tl * C::XT;
+  double *rd = red + (size_t)tl * R::RED_PER_SEQ;  // [2][NW] dsum partials, then [2][5][NW] scan totals
+  const double ends = DIR > 0 ? 2.0 : 1.0;         // the backward transform doubles the end points first
+  for (; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const long long pr = tile * C::TPB + tl;
+    const bool live = act && pr < npairs;
+    double *xa = r + (live ? pr : 0) * 2 * n, *xb = xa + n;
+    cpx a[P];
+    double pa = 0.0, pb = 0.0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const int e = t + NT * i;
+      a[i] = make_double2(0.0, 0.0);
+      if (live) {
+        if (e == 0) a[i] = make_double2(ends * (la[0] + la[n - 1]), ends * (lb[0] + lb[n - 1]));
+        else if (e == N / 2) a[i] = make_double2(la[e] + la[e], lb[e] + lb[e]);
+        else {
+          const int j = e < N / 2 ? e : N - e, jc = N - j;
+          const double t1a = la[j] + la[jc], t2a = la[j] - la[jc], t1b = lb[j] + lb[jc], t2b = lb[j] - lb[jc];
+          const double sj = Ssm[j];
+          if (e < N / 2) {
+            const double cj = Csm[j];
+            pa = fma(cj, t2a, pa);
+            pb = fma(cj, t2b, pb);
+            a[i] = make_double2(fma(-sj, t2a, t1a), fma(-sj, t2b, t1b));
+          } else {
+            a[i] = make_double2(fma(sj, t2a, t1a), fma(sj, t2b, t1b));
+          }
+        }
+      }
+    }
+    const double x0a = live ? ends * la[0] : 0.0, xna = live ? ends * la[n - 1] : 0.0;
+    const double x0b = live ? ends * lb[0] : 0.0, xnb = live ? ends * lb[n - 1] : 0.0;
+    pa = warp_sum(pa);
+    pb = warp_sum(pb);
+    if (lane == 0) {
+      rd[w] = pa;
+      rd[NW + w] = pb;
+    }
+    __syncthreads();  // landing buffer consumed; dsum partials visible
+    const long long next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) issue(next);
+    double dsa = x0a - xna, dsb = x0b - xnb;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      dsa += rd[k];
+      dsb += rd[NW + k];
+    }
+    r10_core<C, 3, -1>(a, xq, t, act, tws);  // forward real transform in both directions (costb1_ calls rfft1f_ too)
+    cpx *zq = (cpx *)xq;
+    if (act) {
+#pragma unroll
+      for (int i = P / 2; i < P; ++i) zq[t + NT * (i - P / 2)] = a[i];
+    }
+    __syncthreads();
+    // h[2f-1] = A_f, h[2f] = B_f (scaled like rfftf1_);  y[2f] = c1 A_f, y[2f-1] = D + sum_{m<f} c1 B_m, y[0] = c0 h[0]
+    const double sc = 1.0 / (double)N;
+    const double c0 = DIR < 0 ? 0.5 : 0.5 * (double)N, c1 = DIR < 0 ? 0.5 : 0.25 * (double)N;
+    const double Da = DIR < 0 ? dsa * sc : 0.5 * dsa, Db = DIR < 0 ? dsb * sc : 0.5 * dsb;
+    double Aa[P / 2], Ab[P / 2], inca[P / 2], incb[P / 2], va_[P / 2], vb_[P / 2];
+    double *tot = rd + 2 * NW;  // [2][5][NW]
+#pragma unroll
+    for (int i = 0; i < P / 2; ++i) {
+      const int f = t + NT * i;
+      const cpx u = a[i], v = act ? zq[f == 0 ? 0 : N / 2 - f] : make_double2(0.0, 0.0);
+      double Ba, Bb;
+      if (f == 0 || !act) {
+        Aa[i] = Ab[i] = 0.0;
+        Ba = Bb = 0.0;  // slot 0 is h[0]: not part of the running sum
+      } else {
+        Aa[i] = (u.x + v.x) * sc;
+        Ba = (v.y - u.y) * sc;
+        Ab[i] = (u.y + v.y) * sc;
+        Bb = (u.x - v.x) * sc;
+      }
+      va_[i] = c1 * Ba;
+      vb_[i] = c1 * Bb;
+      // inclusive scan over the lanes of the warp
+      double sa = va_[i], sb = vb_[i];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double ua = __shfl_up_sync(0xffffffffu, sa, o), ub = __shfl_up_sync(0xffffffffu, sb, o);
+        if (lane >= o) {
+          sa += ua;
+          sb += ub;
+        }
+      }
+      inca[i] = sa;
+      incb[i] = sb;
+      if (lane == 31) {
+        tot[i * NW + w] = sa;
+        tot[5 * NW + i * NW + w] = sb;
+      }
+    }
+    __syncthreads();
+    {
+      double carrya = Da, carryb = Db;  // prefix of everything before block i, warp w
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        double ca = carrya, cb = carryb;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+          const double ta = tot[i * NW + k], tb = tot[5 * NW + i * NW + k];
+          if (k < w) {
+            ca += ta;
+            cb += tb;
+          }
+          carrya += ta;
+          carryb += tb;
+        }
+        const int f = t + NT * i;
+        if (live) {
+          if (f == 0) {
+            xa[0] = c0 * (a[0].x * sc);
+            xb[0] = c0 * (a[0].y * sc);
+          } else {
+            xa[2 * f - 1] = ca + inca[i] - va_[i];
+            xa[2 * f] = c1 * Aa[i];
+            xb[2 * f - 1] = cb + incb[i] - vb_[i];
+            xb[2 * f] = c1 * Ab[i];
+          }
+        }
+      }
+      if (live && t == 0) {  // f = N/2: y[n-2] = D + all of the sum, y[n-1] from X_{N/2}
+        const cpx mid = zq[0];
+        const double lf = DIR < 0 ? c1 : 2.0 * c1;
+        xa[n - 2] = carrya;
+        xa[n - 1] = lf * (mid.x * sc);
+        xb[n - 2] = carryb;
+        xb[n - 1] = lf * (mid.y * sc);
+      }
+    }
+    // zq / tot are rewritten by the next tile only after its landing barrier
+  }
+}
+
 /* host side (radix10.cu) */
 bool r10_supported(int n);
 bool r10_c2c_launch(int n, long long lot, long long jump, int dir, cpx *c, double scale);
 bool r10_r2c_launch(int n, long long lot, long long jump, int dir, double *r);
 bool r10_cosq_launch(int n, long long lot, long long jump, int dir, double *x, const double *trig);
+/* costmf_/costmb_ n = 1001, contiguous rows, an even number of rows */
+bool r10_cost_launch(long long npairs, int dir, double *x, const double *trig);
 
 }  // namespace cfb
 #endif
