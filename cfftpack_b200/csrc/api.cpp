@@ -63,6 +63,22 @@ bool device_ready() {
   return ok;
 }
 
+bool kernel_attrs_ready(const void *kernel, size_t smem) {
+  static std::mutex mu;
+  static std::vector<std::pair<std::pair<const void *, int>, bool>> done;  // few dozen entries: linear search is fine
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto &e : done)
+    if (e.first.first == kernel && e.first.second == dev) return e.second;
+  const bool ok = cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(max dynamic shared memory)") &&
+                  cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
+                          "cudaFuncSetAttribute(shared memory carveout)");
+  done.push_back({{kernel, dev}, ok});
+  return ok;
+}
+
 int sm_count() {
   static int sms = 0;
   if (!sms) {
@@ -78,6 +94,7 @@ int sm_count() {
 struct Scratch {
   void *p = nullptr;
   size_t cap = 0;
+  int dev = -1;
 };
 struct ScratchSet {
   Scratch s[4];
@@ -89,7 +106,9 @@ struct ScratchSet {
 static thread_local ScratchSet t_scr;
 void *scratch_get(int slot, size_t bytes) {
   Scratch &s = t_scr.s[slot];
-  if (s.cap >= bytes && s.p) return s.p;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (s.cap >= bytes && s.p && s.dev == dev) return s.p;
   if (s.p) {
     cudaStreamSynchronize(t_stream);
     cudaFree(s.p);
@@ -102,6 +121,7 @@ void *scratch_get(int slot, size_t bytes) {
     return nullptr;
   }
   s.cap = cap;
+  s.dev = dev;
   return s.p;
 }
 void scratch_release_all() {

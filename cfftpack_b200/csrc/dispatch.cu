@@ -26,18 +26,7 @@ static const size_t SMEM_TARGET = 72 * 1024;    // aim: three CTAs per SM for th
 int engine_max_c2c() { return (int)((SMEM_MAX - 1024) / 48) - 4; }
 int engine_max_real() { return (int)((SMEM_MAX - 1024) / 48) - 4; }
 
-static bool engine_attr_once() {
-  static std::once_flag once;
-  static bool ok = true;
-  std::call_once(once, [] {
-    ok = cuda_ok(cudaFuncSetAttribute(engine_c2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
-                 "cudaFuncSetAttribute(engine_c2c_kernel)") &&
-         cuda_ok(cudaFuncSetAttribute(engine_c2c_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
-                 "cudaFuncSetAttribute(engine_c2c_kernel, carveout)") &&
-         true;
-  });
-  return ok;
-}
+static bool engine_attr_once() { return kernel_attrs_ready((const void *)engine_c2c_kernel, SMEM_MAX); }
 
 static const size_t TW_SMEM_MAX = 16 * 1024;  // plan twiddle tables up to this size are copied to shared memory
 
@@ -73,16 +62,8 @@ static int four_step_split(int n, int limit) {
 /* the real-family kernel is instantiated per (family, direction): the family-specific code folds at compile time */
 template <int KIND, int DIR>
 static bool launch_real_kernel(unsigned grid, unsigned threads, size_t smem, const EngineParams &P) {
-  static std::once_flag once;
-  static bool ok = true;
   auto kern = engine_kernel<KIND, DIR>;
-  std::call_once(once, [&] {
-    ok = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX),
-                 "cudaFuncSetAttribute(engine_kernel)") &&
-         cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
-                 "cudaFuncSetAttribute(engine_kernel, carveout)");
-  });
-  if (!ok) return false;
+  if (!kernel_attrs_ready((const void *)kern, SMEM_MAX)) return false;
   CFB_LAUNCH(kern, grid, threads, smem, current_stream(), P);
   return true;
 }

@@ -18,6 +18,9 @@ void set_current_stream(cudaStream_t s);
 void count_launch(unsigned long long k = 1);
 unsigned long long launch_count();
 
+/* opt a kernel into `smem` bytes of dynamic shared memory and the full shared-memory carveout, once per (kernel, device) */
+bool kernel_attrs_ready(const void *kernel, size_t smem);
+
 /* true once a CUDA device is usable; otherwise prints one loud line to stderr (there is no CPU path) */
 bool device_ready();
 int sm_count();

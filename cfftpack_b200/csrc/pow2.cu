@@ -91,25 +91,16 @@ const cpx *pow2_stream_table() {
 }
 
 template <class K>
-bool set_smem_once(K kernel, size_t smem, std::once_flag &once, bool &ok) {
-  std::call_once(once, [&] {
-    ok = cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                 "cudaFuncSetAttribute(pow2 kernel, smem size)") &&
-         // ask for the full shared-memory carveout: three 68 KiB CTAs only fit next to a minimal L1
-         cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
-                 "cudaFuncSetAttribute(pow2 kernel, carveout)");
-  });
-  return ok;
+bool set_smem_once(K kernel, size_t smem) {
+  return kernel_attrs_ready((const void *)kernel, smem);
 }
 
 template <class C, int MINB, int DIR>
 bool launch_c2c_cfg(long long lot, long long jump, cpx *c, double scale) {
   const cpx *tw = pow2_table<C>();
   if (!tw) return false;
-  static std::once_flag once;
-  static bool ok = true;
   auto kern = pow2_c2c_kernel<C, MINB, DIR>;
-  if (!set_smem_once(kern, C::SMEM, once, ok)) return false;
+  if (!set_smem_once(kern, C::SMEM)) return false;
   const long long grid = (lot + C::TPB - 1) / C::TPB;
   CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, C::SMEM, current_stream(), c, lot, jump, tw, scale);
   count_launch();
@@ -120,10 +111,8 @@ template <class C, int MINB, int DIR>
 bool launch_r2c_cfg(long long lot, long long jump, double *r) {
   const cpx *tw = pow2_table<C>();
   if (!tw) return false;
-  static std::once_flag once;
-  static bool ok = true;
   auto kern = pow2_r2c_kernel<C, MINB, DIR>;
-  if (!set_smem_once(kern, C::SMEM, once, ok)) return false;
+  if (!set_smem_once(kern, C::SMEM)) return false;
   const long long pairs = (lot + 1) / 2;
   const long long grid = (pairs + C::TPB - 1) / C::TPB;
   CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, C::SMEM, current_stream(), r, lot, jump, tw);
@@ -135,10 +124,8 @@ template <class C, int MINB, int DIR>
 bool launch_c2c_stream(long long lot, long long jump, cpx *c, double scale) {
   const cpx *tw = pow2_stream_table<C>();
   if (!tw) return false;
-  static std::once_flag once;
-  static bool ok = true;
   auto kern = pow2_c2c_stream_kernel<C, MINB, DIR>;
-  if (!set_smem_once(kern, StreamSmem<C>::BYTES, once, ok)) return false;
+  if (!set_smem_once(kern, StreamSmem<C>::BYTES)) return false;
   const long long ntiles = (lot + C::TPB - 1) / C::TPB;
   const long long cap = (long long)MINB * sm_count();
   const long long grid = ntiles < cap ? ntiles : cap;
@@ -151,10 +138,8 @@ template <class C, int MINB, int DIR>
 bool launch_r2c_stream(long long lot, long long jump, double *r) {
   const cpx *tw = pow2_stream_table<C>();
   if (!tw) return false;
-  static std::once_flag once;
-  static bool ok = true;
   auto kern = pow2_r2c_stream_kernel<C, MINB, DIR>;
-  if (!set_smem_once(kern, StreamSmem<C>::BYTES, once, ok)) return false;
+  if (!set_smem_once(kern, StreamSmem<C>::BYTES)) return false;
   const long long pairs = (lot + 1) / 2;
   const long long ntiles = (pairs + C::TPB - 1) / C::TPB;
   const long long cap = (long long)MINB * sm_count();
@@ -208,10 +193,8 @@ bool launch_tile_stream(TileParams &P) {
   typedef Pow2Cfg<LOG2N, 4, 1, THREADS> C;
   P.tw = pow2_stream_table<C>();
   if (!P.tw) return false;
-  static std::once_flag once;
-  static bool ok = true;
   auto kern = pow2_tile_stream_kernel<C, DIR>;
-  if (!set_smem_once(kern, SMEM_LIMIT, once, ok)) return false;
+  if (!set_smem_once(kern, SMEM_LIMIT)) return false;
   const size_t smem = TileStreamSmem<C>::bytes(P.fs_count);
   if (smem > SMEM_LIMIT) return false;
   const long long ntiles = (P.lot + C::TPB - 1) / C::TPB;
@@ -235,10 +218,8 @@ bool launch_tile(TileParams &P) {
   typedef Pow2Cfg<LOG2N, 4, 0> C;
   P.tw = pow2_table<C>();
   if (!P.tw) return false;
-  static std::once_flag once;
-  static bool ok = true;
   auto kern = pow2_tile_kernel<C, DIR>;
-  if (!set_smem_once(kern, SMEM_LIMIT, once, ok)) return false;
+  if (!set_smem_once(kern, SMEM_LIMIT)) return false;
   const size_t smem = TileSmem<C>::bytes(P.fs_count);
   if (smem > SMEM_LIMIT) {
     set_error("pow2_tile_kernel: %zu bytes of shared memory", smem);

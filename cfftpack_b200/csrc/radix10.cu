@@ -45,12 +45,8 @@ const cpx *r10_table() {
 }
 
 template <class Kern>
-bool attr_once(Kern kern, size_t smem, std::once_flag &once, bool &ok) {
-  std::call_once(once, [&] {
-    ok = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(r10)") &&
-         cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100), "cudaFuncSetAttribute(r10)");
-  });
-  return ok;
+bool attr_once(Kern kern, size_t smem) {
+  return kernel_attrs_ready((const void *)kern, smem);
 }
 
 template <int K>
@@ -68,10 +64,8 @@ bool launch_c2c(long long lot, long long jump, cpx *c, double scale) {
   typedef R10Cfg<K> C;
   const cpx *tw = r10_table<K>();
   if (!tw) return false;
-  static std::once_flag once;
-  static bool ok = true;
   auto kern = r10_c2c_stream_kernel<K, DIR>;
-  if (!attr_once(kern, C::BYTES, once, ok)) return false;
+  if (!attr_once(kern, C::BYTES)) return false;
   const long long ntiles = (lot + C::TPB - 1) / C::TPB;
   CFB_LAUNCH(kern, (unsigned)grid_for<K>(ntiles), C::THREADS, C::BYTES, current_stream(), c, lot, jump, tw, scale, ntiles);
   count_launch();
@@ -83,11 +77,9 @@ bool launch_r2c(long long lot, long long jump, double *r, const double *trig) {
   typedef R10Cfg<K> C;
   const cpx *tw = r10_table<K>();
   if (!tw) return false;
-  static std::once_flag once;
-  static bool ok = true;
   auto kern = r10_r2c_stream_kernel<K, KIND, DIR>;
   const size_t smem = KIND == K_COSQ ? C::BYTES_TRIG : C::BYTES;
-  if (!attr_once(kern, smem, once, ok)) return false;
+  if (!attr_once(kern, smem)) return false;
   const long long pairs = (lot + 1) / 2;
   const long long ntiles = (pairs + C::TPB - 1) / C::TPB;
   CFB_LAUNCH(kern, (unsigned)grid_for<K>(ntiles), C::THREADS, smem, current_stream(), r, lot, jump, tw, trig, ntiles);
@@ -100,8 +92,6 @@ bool r10_cost_launch(long long npairs, int dir, double *x, const double *trig) {
   typedef R10Cfg<3> C;
   const cpx *tw = r10_table<3>();
   if (!tw) return false;
-  static std::once_flag once_f, once_b;
-  static bool ok_f = true, ok_b = true;
   const long long ntiles = (npairs + C::TPB - 1) / C::TPB;
   long long per_sm = (long long)((SMEM_LIMIT + 1024) / (R10Cost::BYTES + 1024));
   if (per_sm > 2) per_sm = 2;
@@ -109,11 +99,11 @@ bool r10_cost_launch(long long npairs, int dir, double *x, const double *trig) {
   if (grid > ntiles) grid = ntiles;
   if (dir < 0) {
     auto kern = r10_cost_stream_kernel<-1>;
-    if (!attr_once(kern, R10Cost::BYTES, once_f, ok_f)) return false;
+    if (!attr_once(kern, R10Cost::BYTES)) return false;
     CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, R10Cost::BYTES, current_stream(), x, npairs, tw, trig, ntiles);
   } else {
     auto kern = r10_cost_stream_kernel<1>;
-    if (!attr_once(kern, R10Cost::BYTES, once_b, ok_b)) return false;
+    if (!attr_once(kern, R10Cost::BYTES)) return false;
     CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, R10Cost::BYTES, current_stream(), x, npairs, tw, trig, ntiles);
   }
   count_launch();

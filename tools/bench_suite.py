@@ -46,7 +46,35 @@ def case2d(l, m, d="f"):
     by = 2 * 2 * 16 * l * m  # two passes minimum
     print(f"cfft2{d} {l}x{m}: {ms:8.3f} ms  {by / ms / 1e6:8.1f} GB/s vs 2-pass minimum ({by / ms / 1e6 / 65.475:5.1f}% of measured HBM)", flush=True)
 
-which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c2", "c3", "c4", "c5", "misc"]
+def case_c1():
+    """config 1: single cfft1f_/cfft1b_ N=1024 (latency): device pointer (async launch + sync) and host array (staged)"""
+    import numpy as np
+    P = fl.Lib(fl.product())
+    n = 1024
+    ws, _ = P.init("cfft", n)
+    I = ctypes.c_int
+    ier = I(-1); dummy = np.zeros(2 * n + 8)
+    xd = torch.rand(n, 2, device="cuda", dtype=torch.float64)
+    xh = np.random.rand(n).astype(np.complex128)
+    def call(ptr, name):
+        getattr(fl.product(), name)(ctypes.byref(I(n)), ctypes.byref(I(1)), ctypes.c_void_p(ptr), ctypes.byref(I(n)), fl.P(ws),
+                                    ctypes.byref(I(fl.lensav("cfft", n))), fl.P(dummy), ctypes.byref(I(2 * n)), ctypes.byref(ier))
+        assert ier.value == 0
+    for label, ptr, sync in (("device pointer", xd.data_ptr(), True), ("host array", xh.ctypes.data, False)):
+        for _ in range(20):
+            call(ptr, "cfft1f_"); call(ptr, "cfft1b_")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 200
+        for _ in range(reps):
+            call(ptr, "cfft1f_"); call(ptr, "cfft1b_")
+            if sync: torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        print(f"cfft1f+cfft1b N=1024 round trip, {label}: {dt * 1e6:8.1f} us per round trip (2 calls, via ctypes)", flush=True)
+
+which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c1", "c2", "c3", "c4", "c5", "misc"]
+if "c1" in which:
+    case_c1()
 if "c2" in which:
     case("cfft", 4096, 65536); case("cfft", 4096, 65536, d="b")
 if "c3" in which:
