@@ -19,6 +19,7 @@
 #include "../../include/cfftpack_b200.h"
 #include "internal.h"
 #include "plan.h"
+#include "tma.cuh"
 
 namespace cfb {
 
@@ -77,6 +78,46 @@ bool kernel_attrs_ready(const void *kernel, size_t smem) {
                           "cudaFuncSetAttribute(shared memory carveout)");
   done.push_back({{kernel, dev}, ok});
   return ok;
+}
+
+bool make_tensor_map3(TensorMap3 *tm, const void *base, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                      unsigned long long s1, unsigned long long s2, unsigned b0, unsigned b1) {
+#ifdef CFB_SIM
+  tm->base = (const double *)base;
+  tm->dim[0] = d0; tm->dim[1] = d1; tm->dim[2] = d2;
+  tm->stride_bytes[0] = 8; tm->stride_bytes[1] = s1; tm->stride_bytes[2] = s2;
+  tm->box[0] = b0; tm->box[1] = b1; tm->box[2] = 1;
+  return true;
+#else
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = (encode_fn)fn;
+  });
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return false;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1, s2};  // bytes, dims 1 and 2
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return false;
+  }
+  return true;
+#endif
 }
 
 int sm_count() {

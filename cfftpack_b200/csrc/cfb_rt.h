@@ -8,5 +8,10 @@
 #define CFB_DYN_SMEM(name) extern __shared__ __align__(16) char name[]
 #define CFB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
+#ifdef CFB_SIM
+#define CFB_GRID_CONSTANT
+#else
+#define CFB_GRID_CONSTANT __grid_constant__
+#endif
 #include <stdint.h>
 #endif

@@ -208,8 +208,43 @@ bool launch_tile_stream(TileParams &P) {
   return cuda_ok(cudaGetLastError(), "pow2_tile_stream_kernel launch");
 }
 
+/* TMA tensor-box variant: rows contiguous on the input side (jump_lo = 1), tiles never straddle an inner batch group */
+template <int LOG2N, int DIR>
+bool launch_tile_tma(TileParams &P) {
+  typedef Pow2Cfg<LOG2N, 4, 1> C;
+  P.tw = pow2_stream_table<C>();
+  if (!P.tw) return false;
+  auto kern = pow2_tile_tma_kernel<C, DIR>;
+  const size_t smem = TileTmaSmem<C>::bytes(P.fs_count);
+  if (!set_smem_once(kern, SMEM_LIMIT)) return false;
+  TensorMap3 tm;
+  const unsigned long long nlo = (unsigned long long)P.ain.nlo;
+  const unsigned long long nhi = (unsigned long long)((P.lot + P.ain.nlo - 1) / P.ain.nlo);
+  if (!make_tensor_map3(&tm, P.in, 2 * nlo, (unsigned long long)C::N, nhi, (unsigned long long)P.ain.inc * 16,
+                        (unsigned long long)(P.ain.jump_hi ? P.ain.jump_hi : 1) * 16, 2 * C::TPB, C::N))
+    return false;
+  const long long ntiles = (P.lot + C::TPB - 1) / C::TPB;
+  long long per_sm = (long long)((SMEM_LIMIT + 1024) / (smem + 1024));
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = per_sm * sm_count();
+  if (grid > ntiles) grid = ntiles;
+  CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, smem, current_stream(), P, tm, ntiles);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "pow2_tile_tma_kernel launch");
+}
+
 template <int LOG2N, int DIR>
 bool launch_tile(TileParams &P) {
+  {
+    typedef Pow2Cfg<LOG2N, 4, 1> C;
+    static const bool no_tma = getenv("CFB200_TILE_NO_TMA") != nullptr;
+    const bool box_ok = C::N <= 256 && 2 * C::TPB <= 256;
+    const bool layout_ok = !P.in_staged && P.ain.jump_lo == 1 && P.ain.nlo % C::TPB == 0 && P.lot % P.ain.nlo == 0 &&
+                           (((uintptr_t)P.in) & 15) == 0 && P.ain.inc > 0 && P.ain.jump_hi >= 0 &&
+                           (unsigned long long)P.ain.inc * 16 < (1ULL << 40) && (unsigned long long)P.ain.jump_hi * 16 < (1ULL << 40);
+    if (!no_tma && box_ok && layout_ok && TileTmaSmem<C>::bytes(P.fs_count) <= SMEM_LIMIT) return launch_tile_tma<LOG2N, DIR>(P);
+  }
   static const bool direct = getenv("CFB200_TILE_DIRECT") != nullptr;
   static const bool wide = getenv("CFB200_TILE_WIDE") != nullptr;  // experiment: 512-thread CTAs, twice the rows per tile
   if (wide && LOG2N <= 7 && TileStreamSmem<Pow2Cfg<LOG2N, 4, 1, 512>>::bytes(P.fs_count) <= SMEM_LIMIT)

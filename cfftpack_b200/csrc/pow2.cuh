@@ -712,6 +712,94 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS > 256 ? 1 : 2)) pow2_t
   cp_async_wait<0>();
 }
 
+/* TMA form of the streaming tile kernel for the layouts whose ROWS are the contiguous axis (three of the four sweeps of
+ * cfft2f_, all sweeps of batch-contiguous layouts): the whole strided tile -- TPB adjacent rows x N elements -- is one
+ * 3-D tensor box, so a single cp.async.bulk.tensor instruction (UTMALDG) per tile replaces 16 LDGSTS per thread.
+ * The box lands dense as [N][TPB] complex; thread (row tl, slot t) reads element e at land[e*TPB + tl]. */
+template <class C>
+struct TileTmaSmem {
+  typedef StreamSmem<C> S;
+  static constexpr int XPITCH = S::XTILE | 1;
+  static constexpr size_t LAND = (size_t)C::TPB * C::N * sizeof(cpx);
+  static constexpr size_t XCH = (size_t)C::TPB * XPITCH * sizeof(double);
+  static constexpr size_t bytes(int fs_count) { return 128 + LAND + XCH + S::TWS + 16 + (size_t)fs_count * sizeof(cpx) + 64; }
+};
+
+template <class C, int DIR>
+__global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_tma_kernel(const TileParams P, const CFB_GRID_CONSTANT TensorMap3 tmap,
+                                                                      long long ntiles) {
+  CFB_DYN_SMEM(smem_raw);
+  typedef TileTmaSmem<C> TS;
+  typedef StreamSmem<C> S;
+  constexpr int PP = C::P, NT = C::NT, TPB = C::TPB, N = C::N;
+  char *base = (char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);  // the tensor box must land 128-byte aligned
+  cpx *land = (cpx *)base;
+  double *xch = (double *)(base + TS::LAND);
+  cpx *tws = (cpx *)(base + TS::LAND + TS::XCH);
+  uint64_t *bar = (uint64_t *)(base + TS::LAND + TS::XCH + S::TWS);
+  cpx *fss = (cpx *)(bar + 2);
+  const int tid = threadIdx.x, tl = tid % TPB, t = tid / TPB;
+  if (tid == 0) mbar_init(bar, 1);
+  for (int i = tid; i < S::TWS_COUNT; i += C::THREADS) tws[i] = __ldg(P.tw + i);
+  for (int i = tid; i < P.fs_count; i += C::THREADS) fss[i] = __ldg(P.fs + i);
+  __syncthreads();
+  const int nlo = P.ain.nlo;
+  auto issue = [&](long long tile) {  // thread 0
+    const long long g0 = tile * TPB;
+    const long long hi = g0 / nlo, lo = g0 - hi * nlo;
+    mbar_expect_tx(bar, (unsigned)(TPB * N * sizeof(cpx)));
+    tma_load_3d(land, &tmap, bar, (int)(2 * lo), 0, (int)hi);
+  };
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) issue(tile);
+  unsigned parity = 0;
+  double *xr = xch + (size_t)tl * TS::XPITCH;
+  for (; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const long long g = tile * TPB + tl;
+    const bool live = g < P.lot;
+    cpx a[PP];
+#pragma unroll
+    for (int i = 0; i < PP; ++i) a[i] = land[(size_t)(t + NT * i) * TPB + tl];
+    __syncthreads();  // landing buffer consumed: refill it while we compute
+    const long long next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) issue(next);
+    pow2_core_split<C, DIR, false>(a, xr, t, tws);
+    if (live) {
+      const long long oout = tile_batch_off(P.aout, g);
+      const double scale = P.scale;
+      if (P.npeers > 0) {
+        const int emask = (1 << P.peer_shift) - 1;
+#pragma unroll
+        for (int i = 0; i < PP; ++i) {
+          const int e = t + NT * i;
+          cpx *dst = P.peers[e >> P.peer_shift] + P.out_base + oout + (long long)(e & emask) * P.aout.inc;
+          *dst = make_double2(a[i].x * scale, a[i].y * scale);
+        }
+      } else {
+        cpx *y = P.out + oout + (long long)t * P.aout.inc;
+        const long long st = (long long)NT * P.aout.inc;
+        if (P.fs_count > 0) {
+          const int j = (int)(P.fs_from_hi ? g / P.aout.nlo : g % P.aout.nlo);
+          const int mask = (1 << P.fs_shift) - 1, sh = P.fs_shift, nmask = P.fs_nmask;
+          auto root = [&](int x) { return cmul(fss[x & mask], fss[mask + 1 + (x >> sh)]); };
+          const cpx b0 = root(j * t), w1 = root((j * NT) & nmask), w4 = root((4 * j * NT) & nmask);
+          cpx b[PP];
+#pragma unroll
+          for (int i = 0; i < PP; ++i) b[i] = b0;
+          twiddle_powers<-1>(b, w1, w4);
+#pragma unroll
+          for (int i = 0; i < PP; ++i) y[i * st] = ctw<DIR>(make_double2(a[i].x * scale, a[i].y * scale), b[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < PP; ++i) y[i * st] = make_double2(a[i].x * scale, a[i].y * scale);
+        }
+      }
+    }
+  }
+}
+
 /* ---- host side ---- */
 bool pow2_c2c_supported(int n, long long inc, long long jump, int aligned16);
 bool pow2_r2c_supported(int n, long long inc, long long jump, int aligned16);

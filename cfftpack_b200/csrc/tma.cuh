@@ -8,7 +8,26 @@
 #define CFB_TMA_CUH
 #include "cfb_rt.h"
 
+#ifndef CFB_SIM
+#include <cuda.h>
+#endif
+
 namespace cfb {
+
+/* 3-D tiled tensor map (TMA descriptor) over an array of doubles: dims/strides outermost last.  In CUDA builds this is
+ * the driver's CUtensorMap; the emulator keeps the geometry and copies the box itself. */
+#ifdef CFB_SIM
+struct TensorMap3 {
+  const double *base;
+  unsigned long long dim[3], stride_bytes[3];  // stride_bytes[0] unused (contiguous)
+  unsigned box[3];
+};
+#else
+typedef CUtensorMap TensorMap3;
+#endif
+/* host: describe `base` as dim0 x dim1 x dim2 doubles with byte strides s1, s2 (multiples of 16) and a box b0 x b1 x 1 */
+bool make_tensor_map3(TensorMap3 *tm, const void *base, unsigned long long d0, unsigned long long d1,
+                      unsigned long long d2, unsigned long long s1, unsigned long long s2, unsigned b0, unsigned b1);
 
 #ifdef CFB_SIM
 /* emulated transaction barrier: low word = completed phases, high word = bytes still expected */
@@ -28,6 +47,22 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
 }
 __device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
   bulk_g2s(smem_dst, gsrc, bytes, bar);
+}
+/* box load: dense [box1][box0] doubles at smem_dst, zero fill outside the tensor */
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const TensorMap3 *tm, uint64_t *bar, int c0, int c1, int c2) {
+  double *d = (double *)smem_dst;
+  unsigned bytes = 0;
+  for (unsigned y = 0; y < tm->box[1]; ++y)
+    for (unsigned x = 0; x < tm->box[0]; ++x) {
+      const unsigned long long i0 = (unsigned long long)c0 + x, i1 = (unsigned long long)c1 + y, i2 = (unsigned long long)c2;
+      double v = 0.0;
+      if (i0 < tm->dim[0] && i1 < tm->dim[1] && i2 < tm->dim[2])
+        v = *(const double *)((const char *)tm->base + i0 * 8 + i1 * tm->stride_bytes[1] + i2 * tm->stride_bytes[2]);
+      d[y * tm->box[0] + x] = v;
+      bytes += 8;
+    }
+  *bar -= (uint64_t)bytes << 32;
+  if ((*bar >> 32) == 0) *bar += 1;
 }
 /* Ampere-style per-thread asynchronous copies (LDGSTS): gathers with arbitrary addresses, no register staging */
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
@@ -65,6 +100,14 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+/* TMA tensor box load (SASS UTMALDG): one instruction moves the whole strided tile */
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const TensorMap3 *tm, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
   // .ca: the two 16-byte halves of a 32-byte sector requested by neighbouring lanes merge in L1 (with .cg every
