@@ -209,18 +209,19 @@ bool launch_tile_stream(TileParams &P) {
 }
 
 /* TMA tensor-box variant: rows contiguous on the input side (jump_lo = 1), tiles never straddle an inner batch group */
-template <int LOG2N, int DIR>
+template <int LOG2N, int DIR, bool STAGED>
 bool launch_tile_tma(TileParams &P) {
   typedef Pow2Cfg<LOG2N, 4, 1> C;
   P.tw = pow2_stream_table<C>();
   if (!P.tw) return false;
-  auto kern = pow2_tile_tma_kernel<C, DIR>;
-  const size_t smem = TileTmaSmem<C>::bytes(P.fs_count);
+  auto kern = pow2_tile_tma_kernel<C, DIR, STAGED>;
+  const size_t smem = TileTmaSmem<C, STAGED>::bytes(P.fs_count);
   if (!set_smem_once(kern, SMEM_LIMIT)) return false;
   TensorMap3 tm;
+  memset(&tm, 0, sizeof(tm));
   const unsigned long long nlo = (unsigned long long)P.ain.nlo;
   const unsigned long long nhi = (unsigned long long)((P.lot + P.ain.nlo - 1) / P.ain.nlo);
-  if (!make_tensor_map3(&tm, P.in, 2 * nlo, (unsigned long long)C::N, nhi, (unsigned long long)P.ain.inc * 16,
+  if (!STAGED && !make_tensor_map3(&tm, P.in, 2 * nlo, (unsigned long long)C::N, nhi, (unsigned long long)P.ain.inc * 16,
                         (unsigned long long)(P.ain.jump_hi ? P.ain.jump_hi : 1) * 16, 2 * C::TPB, C::N))
     return false;
   const long long ntiles = (P.lot + C::TPB - 1) / C::TPB;
@@ -243,7 +244,10 @@ bool launch_tile(TileParams &P) {
     const bool layout_ok = !P.in_staged && P.ain.jump_lo == 1 && P.ain.nlo % C::TPB == 0 && P.lot % P.ain.nlo == 0 &&
                            (((uintptr_t)P.in) & 15) == 0 && P.ain.inc > 0 && P.ain.jump_hi >= 0 &&
                            (unsigned long long)P.ain.inc * 16 < (1ULL << 40) && (unsigned long long)P.ain.jump_hi * 16 < (1ULL << 40);
-    if (!no_tma && box_ok && layout_ok && TileTmaSmem<C>::bytes(P.fs_count) <= SMEM_LIMIT) return launch_tile_tma<LOG2N, DIR>(P);
+    if (!no_tma && box_ok && layout_ok && TileTmaSmem<C, false>::bytes(P.fs_count) <= SMEM_LIMIT)
+      return launch_tile_tma<LOG2N, DIR, false>(P);
+    const bool rows_ok = P.in_staged && P.ain.inc == 1 && (((uintptr_t)P.in) & 15) == 0;
+    if (!no_tma && rows_ok && TileTmaSmem<C, true>::bytes(P.fs_count) <= SMEM_LIMIT) return launch_tile_tma<LOG2N, DIR, true>(P);
   }
   static const bool direct = getenv("CFB200_TILE_DIRECT") != nullptr;
   static const bool wide = getenv("CFB200_TILE_WIDE") != nullptr;  // experiment: 512-thread CTAs, twice the rows per tile

@@ -716,20 +716,21 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS > 256 ? 1 : 2)) pow2_t
  * cfft2f_, all sweeps of batch-contiguous layouts): the whole strided tile -- TPB adjacent rows x N elements -- is one
  * 3-D tensor box, so a single cp.async.bulk.tensor instruction (UTMALDG) per tile replaces 16 LDGSTS per thread.
  * The box lands dense as [N][TPB] complex; thread (row tl, slot t) reads element e at land[e*TPB + tl]. */
-template <class C>
+template <class C, bool STAGED>
 struct TileTmaSmem {
   typedef StreamSmem<C> S;
   static constexpr int XPITCH = S::XTILE | 1;
-  static constexpr size_t LAND = (size_t)C::TPB * C::N * sizeof(cpx);
+  static constexpr int LPITCH = C::N + 1;  // STAGED: one padded landing row per sequence
+  static constexpr size_t LAND = (size_t)C::TPB * (STAGED ? LPITCH : C::N) * sizeof(cpx);
   static constexpr size_t XCH = (size_t)C::TPB * XPITCH * sizeof(double);
   static constexpr size_t bytes(int fs_count) { return 128 + LAND + XCH + S::TWS + 16 + (size_t)fs_count * sizeof(cpx) + 64; }
 };
 
-template <class C, int DIR>
+template <class C, int DIR, bool STAGED>
 __global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_tma_kernel(const TileParams P, const CFB_GRID_CONSTANT TensorMap3 tmap,
                                                                       long long ntiles) {
   CFB_DYN_SMEM(smem_raw);
-  typedef TileTmaSmem<C> TS;
+  typedef TileTmaSmem<C, STAGED> TS;
   typedef StreamSmem<C> S;
   constexpr int PP = C::P, NT = C::NT, TPB = C::TPB, N = C::N;
   char *base = (char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);  // the tensor box must land 128-byte aligned
@@ -744,14 +745,24 @@ __global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_tma_kernel(const Tile
   for (int i = tid; i < P.fs_count; i += C::THREADS) fss[i] = __ldg(P.fs + i);
   __syncthreads();
   const int nlo = P.ain.nlo;
-  auto issue = [&](long long tile) {  // thread 0
+  auto issue = [&](long long tile) {  // warp 0
     const long long g0 = tile * TPB;
-    const long long hi = g0 / nlo, lo = g0 - hi * nlo;
-    mbar_expect_tx(bar, (unsigned)(TPB * N * sizeof(cpx)));
-    tma_load_3d(land, &tmap, bar, (int)(2 * lo), 0, (int)hi);
+    if (!STAGED) {
+      if (tid == 0) {
+        const long long hi = g0 / nlo, lo = g0 - hi * nlo;
+        mbar_expect_tx(bar, (unsigned)(TPB * N * sizeof(cpx)));
+        tma_load_3d(land, &tmap, bar, (int)(2 * lo), 0, (int)hi);
+      }
+    } else {  // every sequence is one contiguous run: a 1-D bulk copy per row into its padded landing row
+      const long long rows = P.lot - g0 < TPB ? P.lot - g0 : TPB;
+      if (tid == 0) mbar_expect_tx(bar, (unsigned)(rows * N * sizeof(cpx)));
+      __syncwarp();
+      for (int r = tid; r < rows; r += 32)
+        bulk_g2s(land + (size_t)r * TS::LPITCH, P.in + tile_batch_off(P.ain, g0 + r), (unsigned)(N * sizeof(cpx)), bar);
+    }
   };
   long long tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) issue(tile);
+  if (tid < 32 && tile < ntiles) issue(tile);
   unsigned parity = 0;
   double *xr = xch + (size_t)tl * TS::XPITCH;
   for (; tile < ntiles; tile += gridDim.x) {
@@ -761,10 +772,10 @@ __global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_tma_kernel(const Tile
     const bool live = g < P.lot;
     cpx a[PP];
 #pragma unroll
-    for (int i = 0; i < PP; ++i) a[i] = land[(size_t)(t + NT * i) * TPB + tl];
+    for (int i = 0; i < PP; ++i) a[i] = STAGED ? land[(size_t)tl * TS::LPITCH + t + NT * i] : land[(size_t)(t + NT * i) * TPB + tl];
     __syncthreads();  // landing buffer consumed: refill it while we compute
     const long long next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) issue(next);
+    if (tid < 32 && next < ntiles) issue(next);
     pow2_core_split<C, DIR, false>(a, xr, t, tws);
     if (live) {
       const long long oout = tile_batch_off(P.aout, g);
