@@ -138,7 +138,7 @@ struct Scratch {
   int dev = -1;
 };
 struct ScratchSet {
-  Scratch s[4];
+  Scratch s[8];  // 0 four-step, 1 staged host array, 2 chirp-z, 3 long real, 4-6 staging pipeline, 7 rfft2 pairs
   ~ScratchSet() {
     for (auto &x : s)
       if (x.p) cudaFree(x.p);
@@ -254,7 +254,7 @@ static bool run_on_array(void *user, size_t esz, long long lot, long long jump, 
   const size_t buf_bytes = (size_t)((per - 1) * jump + seq_span) * esz;
   void *bufs[PIPE_BUFS];
   for (int i = 0; i < PIPE_BUFS; ++i)
-    if (!(bufs[i] = scratch_get(1 + i, buf_bytes))) return false;
+    if (!(bufs[i] = scratch_get(4 + i, buf_bytes))) return false;
   cudaStream_t saved = t_stream;
   if (!cuda_ok(cudaStreamSynchronize(saved), "cudaStreamSynchronize")) return false;
   bool ok = true;
@@ -328,6 +328,28 @@ static int complex_2d(int *ldim, int *l, int *m, void *c, int *lensav, int *lenw
   DeviceView v;
   bool ok = view_open(c, ((size_t)*ldim * (*m - 1) + *l) * 16, v);
   if (ok) ok = run_c2c_2d(*ldim, *l, *m, dir, v.dev);
+  ok = view_close(v, ok);
+  if (!ok) *ier = -1;
+  return 0;
+}
+
+/* rfft2 (fftpack.c:13113-13508): wsave = [rfft plan of l | cfft plan of m | rfft plan of m] */
+static void real_2d_sizes(int l, int m, int &lw, int &mw, int &mm) {
+  lw = l + log2_floor_ref(l) + 4;
+  mw = 2 * m + log2_floor_ref(m) + 4;
+  mm = m + log2_floor_ref(m) + 4;
+}
+static int real_2d(int *ldim, int *l, int *m, double *r, int *lensav, int *lenwrk, int *ier, int dir) {
+  int lw, mw, mm;
+  *ier = 0;
+  real_2d_sizes(*l, *m, lw, mw, mm);
+  if (*lensav < lw + mw + mm) *ier = 2;
+  else if ((long long)*lenwrk < ((long long)*l + 1) * *m) *ier = 3;
+  else if (*ldim < *l) *ier = 5;
+  if (*ier) return 0;
+  DeviceView v;
+  bool ok = view_open(r, ((size_t)*ldim * (*m - 1) + *l) * 8, v);
+  if (ok) ok = run_real_2d(*ldim, *l, *m, dir, (double *)v.dev);
   ok = view_close(v, ok);
   if (!ok) *ier = -1;
   return 0;
@@ -442,6 +464,27 @@ int cfft2f_(int *ldim, int *l, int *m, fft_complex_t *c, double *, int *lensav, 
 }
 int cfft2b_(int *ldim, int *l, int *m, fft_complex_t *c, double *, int *lensav, double *, int *lenwrk, int *ier) {
   return complex_2d(ldim, l, m, c, lensav, lenwrk, ier, +1);
+}
+
+int rfft2i_(int *l, int *m, double *wsave, int *lensav, int *ier) {
+  int lw, mw, mm, ier1 = 0;
+  *ier = 0;
+  real_2d_sizes(*l, *m, lw, mw, mm);
+  if (*lensav < lw + mw + mm) {
+    *ier = 2;
+    return 0;
+  }
+  real_init(K_RFFT, l, wsave, &lw, &ier1);
+  if (!ier1) complex_init(m, wsave + lw, &mw, &ier1);
+  if (!ier1) real_init(K_RFFT, m, wsave + lw + mw, &mm, &ier1);
+  if (ier1) *ier = 20;
+  return 0;
+}
+int rfft2f_(int *ldim, int *l, int *m, double *r, double *, int *lensav, double *, int *lenwrk, int *ier) {
+  return real_2d(ldim, l, m, r, lensav, lenwrk, ier, -1);
+}
+int rfft2b_(int *ldim, int *l, int *m, double *r, double *, int *lensav, double *, int *lenwrk, int *ier) {
+  return real_2d(ldim, l, m, r, lensav, lenwrk, ier, +1);
 }
 
 #define CFB_DEF_REAL(name, K)                                                                                          \

@@ -429,6 +429,86 @@ bool run_c2c_2d(int ldim, int l, int m, int dir, void *c) {
   return run_c2c(l, m, 1, ldim, dir, c);
 }
 
+/* ---- rfft2f_/rfft2b_ (fftpack.c:13282, :13113).  Columns become half-complex vectors along i; the (Re, Im) row pairs
+ * f = 1..(l-1)/2 are gathered into a compact complex array W(f-1, j) -- the conversion between FFTPACK's (2/N cos, 2/N
+ * sin) and plain (Re, Im)/N, a factor 1/2 and a sign, rides on that copy -- transformed along j as one batched complex
+ * transform, and scattered back; rows 0 and (l even) l-1 are real along j.  The reference instead copies the whole
+ * array into `work` and sweeps r three more times for the conversions (:13383-13395, r2w_/w2r_). ---- */
+struct Real2dParams {
+  double *r;
+  cpx *w;
+  long long ldim;
+  int lotc, m;
+  double sre, sim;
+};
+__global__ void __launch_bounds__(256) rfft2_gather_kernel(const Real2dParams P) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;  // pair index f+1
+  if (f >= P.lotc) return;
+  for (int j = blockIdx.y; j < P.m; j += gridDim.y) {
+    const double *col = P.r + (long long)j * P.ldim + 2 * f + 1;
+    P.w[(long long)j * P.lotc + f] = make_double2(col[0] * P.sre, col[1] * P.sim);
+  }
+}
+__global__ void __launch_bounds__(256) rfft2_scatter_kernel(const Real2dParams P) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= P.lotc) return;
+  for (int j = blockIdx.y; j < P.m; j += gridDim.y) {
+    const cpx v = P.w[(long long)j * P.lotc + f];
+    double *col = P.r + (long long)j * P.ldim + 2 * f + 1;
+    col[0] = v.x * P.sre;
+    col[1] = v.y * P.sim;
+  }
+}
+/* one strided line of length len: x[k] *= s for 0 < k < 2*((len+1)/2) - 1, sign flipped at even k >= 2 */
+__global__ void __launch_bounds__(256) rfft2_line_kernel(double *x, long long stride, int len, double s) {
+  const int top = 2 * ((len + 1) / 2) - 1;
+  for (int k = 1 + blockIdx.x * blockDim.x + threadIdx.x; k < top; k += gridDim.x * blockDim.x)
+    x[(long long)k * stride] *= (k & 1) ? s : -s;
+}
+
+bool run_real_2d(int ldim, int l, int m, int dir, double *r) {
+  cudaStream_t st = current_stream();
+  const int lotc = (l + 1) / 2 - 1;
+  auto line = [&](double *row, double s) {
+    if (2 * ((m + 1) / 2) - 1 <= 1) return true;  // nothing between the mean and the Nyquist term
+    const unsigned g = (unsigned)((m + 255) / 256 < 64 ? (m + 255) / 256 : 64);
+    CFB_LAUNCH(rfft2_line_kernel, g, 256, 0, st, row, (long long)ldim, m, s);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "rfft2_line_kernel");
+  };
+  auto rows_along_j = [&](double *row) {  // one real transform of length m, stride ldim
+    if (dir < 0) return (m == 1 || run_real(K_RFFT, m, 1, ldim, 1, -1, row)) && line(row, 0.5);
+    return line(row, 2.0) && (m == 1 || run_real(K_RFFT, m, 1, ldim, 1, +1, row));
+  };
+  Real2dParams P;
+  memset(&P, 0, sizeof(P));
+  P.r = r;
+  P.ldim = ldim;
+  P.lotc = lotc;
+  P.m = m;
+  const dim3 grid((unsigned)((lotc + 255) / 256), (unsigned)(m < 4096 ? m : 4096));
+  if (dir < 0 && l > 1 && !run_real(K_RFFT, l, m, 1, ldim, -1, r)) return false;
+  if (!rows_along_j(r)) return false;
+  if (l % 2 == 0 && !rows_along_j(r + (l - 1))) return false;
+  if (lotc > 0) {
+    P.w = (cpx *)scratch_get(7, (size_t)lotc * m * sizeof(cpx));
+    if (!P.w) return false;
+    P.sre = dir < 0 ? 0.5 : 1.0;
+    P.sim = dir < 0 ? -0.5 : 1.0;
+    CFB_LAUNCH(rfft2_gather_kernel, grid, 256, 0, st, P);
+    count_launch();
+    if (!cuda_ok(cudaGetLastError(), "rfft2_gather_kernel")) return false;
+    if (m > 1 && !run_c2c(m, lotc, lotc, 1, dir, P.w)) return false;
+    P.sre = dir < 0 ? 1.0 : 2.0;
+    P.sim = dir < 0 ? 1.0 : -2.0;
+    CFB_LAUNCH(rfft2_scatter_kernel, grid, 256, 0, st, P);
+    count_launch();
+    if (!cuda_ok(cudaGetLastError(), "rfft2_scatter_kernel")) return false;
+  }
+  if (dir > 0 && l > 1 && !run_real(K_RFFT, l, m, 1, ldim, +1, r)) return false;
+  return true;
+}
+
 /* real-family sequences too long for one CTA: global-memory pipeline around the long complex transform */
 static int long_real_threshold() {
   static int v = -1;

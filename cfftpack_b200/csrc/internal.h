@@ -34,6 +34,7 @@ bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void 
 bool run_c2c_scaled(int n, long long lot, long long inc, long long jump, int dir, void *c, double scale);
 bool run_real(int kind, int n, long long lot, long long inc, long long jump, int dir, double *x);
 bool run_c2c_2d(int ldim, int l, int m, int dir, void *c);
+bool run_real_2d(int ldim, int l, int m, int dir, double *r);
 bool run_c2c_2d_sharded_phase(int phase, int dir, int l, int m, int rank, int nranks, void *src, void *const *peers);
 
 /* largest core length the single-kernel paths take (for tests and docs) */

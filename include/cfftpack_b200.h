@@ -45,6 +45,14 @@ int cfft2i_(int *l, int *m, fft_real_t *wsave, int *lensav, int *ier);
 int cfft2f_(int *ldim, int *l, int *m, fft_complex_t *c, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
 int cfft2b_(int *ldim, int *l, int *m, fft_complex_t *c, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
 
+/* ---- real 2-D: fftpack.c:13454 (rfft2i_), :13282 (rfft2f_), :13113 (rfft2b_); exported, not in fftpack.h.
+ * r(ldim, m) real column-major; result along i in half-complex order [Re0, Re1, Im1, ...] of X/(l*m), rows 0 and
+ * (l even) l-1 half-complex along j as well.  lensav >= l+L2(l)+4 + 2m+L2(m)+4 + m+L2(m)+4, lenwrk >= (l+1)*m.
+ * Unlike the reference (which uses r as scratch, :13407) rows l..ldim-1 of r are left untouched. ---- */
+int rfft2i_(int *l, int *m, fft_real_t *wsave, int *lensav, int *ier);
+int rfft2f_(int *ldim, int *l, int *m, fft_real_t *r, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+int rfft2b_(int *ldim, int *l, int *m, fft_real_t *r, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);
+
 /* ---- real 1-D: cfftpack/fftpack.h:150-157, fftpack.c:13076 (rfft1i_), :13030 (rfft1f_), :12984 (rfft1b_) ---- */
 int rfft1i_(int *n, fft_real_t *wsave, int *lensav, int *ier);
 int rfft1f_(int *n, int *inc, fft_real_t *r, int *lenr, fft_real_t *wsave, int *lensav, fft_real_t *work, int *lenwrk, int *ier);

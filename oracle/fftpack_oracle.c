@@ -503,6 +503,91 @@ int orc_cfft2b_(int *ldim, int *l, int *m, cpx *c, double *wsave, int *lensav, d
   return c_fft2(ldim, l, m, c, wsave, lensav, work, lenwrk, ier, +1);
 }
 
+/* 2-D real: fftpack.c:13113-13508 (rfft2b_, rfft2f_, rfft2i_) with the copies r2w_/w2r_ (:12949, :15175).
+ * wsave = [rfft plan of l | cfft plan of m | rfft plan of m].  The array is real column-major r(ldim, m); each column
+ * becomes a half-complex vector along i, then rows i=0 (and i=l-1 when l is even) get a real transform along j and
+ * the (Re, Im) row pairs in between a complex one, run on a copy w(2*((l+1)/2), m) so that pairs are complex-aligned. */
+static void rfft2_sizes(int l, int m, int *lw, int *mw, int *mm) {
+  *lw = l + il2(l) + 4;
+  *mw = 2 * m + il2(m) + 4;
+  *mm = m + il2(m) + 4;
+}
+int orc_rfft2i_(int *l, int *m, double *wsave, int *lensav, int *ier) {
+  int lw, mw, mm, ier1;
+  *ier = 0;
+  rfft2_sizes(*l, *m, &lw, &mw, &mm);
+  if (*lensav < lw + mw + mm) { *ier = 2; return 0; }
+  orc_rfftmi_(l, wsave, &lw, &ier1);
+  if (ier1) { *ier = 20; return 0; }
+  orc_cfftmi_(m, wsave + lw, &mw, &ier1);
+  if (ier1) { *ier = 20; return 0; }
+  orc_rfftmi_(m, wsave + lw + mw, &mm, &ier1);
+  if (ier1) *ier = 20;
+  return 0;
+}
+/* half-complex (FFTPACK 2/N cos, 2/N sin) <-> plain (Re, Im)/N along one strided line of length len */
+static void hc_halve(double *x, int stride, int len) {
+  int top = 2 * ((len + 1) / 2) - 1, k;
+  for (k = 1; k < top; ++k) x[(long)k * stride] *= 0.5;
+  for (k = 2; k < len; k += 2) x[(long)k * stride] = -x[(long)k * stride];
+}
+static void hc_double(double *x, int stride, int len) {
+  int top = 2 * ((len + 1) / 2) - 1, k;
+  for (k = 1; k < top; ++k) x[(long)k * stride] += x[(long)k * stride];
+  for (k = 2; k < len; k += 2) x[(long)k * stride] = -x[(long)k * stride];
+}
+static int r_fft2(int *ldim, int *l, int *m, double *r, double *wsave, int *lensav, double *work, int *lenwrk, int *ier,
+                  int fwd) {
+  int lw, mw, mm, one = 1, ier1 = 0, lenr = *m * *ldim, ldh = (*l + 1) / 2, ldw = 2 * ldh, i, j;
+  *ier = 0;
+  rfft2_sizes(*l, *m, &lw, &mw, &mm);
+  if (*lensav < lw + mw + mm) { *ier = 2; return 0; }
+  if (*lenwrk < (*l + 1) * *m) { *ier = 3; return 0; }
+  if (*ldim < *l) { *ier = 5; return 0; }
+  if (fwd) {
+    orc_rfftmf_(m, ldim, l, &one, r, &lenr, wsave, &lw, work, lenwrk, &ier1);
+    if (ier1) { *ier = 20; return 0; }
+    for (j = 0; j < *m; ++j) hc_halve(r + (long)j * *ldim, 1, *l);
+    orc_rfftmf_(&one, &one, m, ldim, r, &lenr, wsave + lw + mw, &mm, work, lenwrk, &ier1);
+    hc_halve(r, *ldim, *m);
+  } else {
+    hc_double(r, *ldim, *m);
+    orc_rfftmb_(&one, &one, m, ldim, r, &lenr, wsave + lw + mw, &mm, work, lenwrk, &ier1);
+  }
+  if (ldh > 1) {
+    int lot = ldh - 1, lenc = ldh * *m, lwk = *l * *m;
+    for (j = 0; j < *m; ++j)
+      for (i = 0; i < *l; ++i) work[i + (long)j * ldw] = r[i + (long)j * *ldim];
+    if (fwd) orc_cfftmf_(&lot, &one, m, &ldh, (cpx *)(work + 1), &lenc, wsave + lw, &mw, r, &lwk, &ier1);
+    else orc_cfftmb_(&lot, &one, m, &ldh, (cpx *)(work + 1), &lenc, wsave + lw, &mw, r, &lwk, &ier1);
+    if (ier1) { *ier = 20; return 0; }
+    for (j = 0; j < *m; ++j)
+      for (i = 0; i < *l; ++i) r[i + (long)j * *ldim] = work[i + (long)j * ldw];
+  }
+  if (*l % 2 == 0) {
+    double *ny = r + (*l - 1);
+    if (fwd) {
+      orc_rfftmf_(&one, &one, m, ldim, ny, &lenr, wsave + lw + mw, &mm, work, lenwrk, &ier1);
+      hc_halve(ny, *ldim, *m);
+    } else {
+      hc_double(ny, *ldim, *m);
+      orc_rfftmb_(&one, &one, m, ldim, ny, &lenr, wsave + lw + mw, &mm, work, lenwrk, &ier1);
+    }
+  }
+  if (!fwd) {
+    for (j = 0; j < *m; ++j) hc_double(r + (long)j * *ldim, 1, *l);
+    orc_rfftmb_(m, ldim, l, &one, r, &lenr, wsave, &lw, work, lenwrk, &ier1);
+  }
+  if (ier1) *ier = 20;
+  return 0;
+}
+int orc_rfft2f_(int *ldim, int *l, int *m, double *r, double *wsave, int *lensav, double *work, int *lenwrk, int *ier) {
+  return r_fft2(ldim, l, m, r, wsave, lensav, work, lenwrk, ier, 1);
+}
+int orc_rfft2b_(int *ldim, int *l, int *m, double *r, double *wsave, int *lensav, double *work, int *lenwrk, int *ier) {
+  return r_fft2(ldim, l, m, r, wsave, lensav, work, lenwrk, ier, 0);
+}
+
 /* ------------------------------------------------------------------ */
 /* public real API: fftpack.c:12984-13112, 13984-14122 */
 int orc_rfft1i_(int *n, double *wsave, int *lensav, int *ier) {

@@ -41,6 +41,10 @@ int orc_cfftmb_(int *lot, int *jump, int *n, int *inc, orc_complex_t *c, int *le
 int orc_cfft2i_(int *l, int *m, double *wsave, int *lensav, int *ier);
 int orc_cfft2f_(int *ldim, int *l, int *m, orc_complex_t *c, double *wsave, int *lensav, double *work, int *lenwrk, int *ier);
 int orc_cfft2b_(int *ldim, int *l, int *m, orc_complex_t *c, double *wsave, int *lensav, double *work, int *lenwrk, int *ier);
+/* fftpack.c:13454, :13282, :13113 */
+int orc_rfft2i_(int *l, int *m, double *wsave, int *lensav, int *ier);
+int orc_rfft2f_(int *ldim, int *l, int *m, double *r, double *wsave, int *lensav, double *work, int *lenwrk, int *ier);
+int orc_rfft2b_(int *ldim, int *l, int *m, double *r, double *wsave, int *lensav, double *work, int *lenwrk, int *ier);
 
 /* real 1-D / multi (fftpack.c:12984-13112, 13984-14122) */
 int orc_rfft1i_(int *n, double *wsave, int *lensav, int *ier);

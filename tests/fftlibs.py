@@ -153,6 +153,39 @@ class Lib:
         return y, ier.value
 
 
+    def init2r(self, l, m):
+        """rfft2i_ (fftpack.c:13454): wsave = rfft plan of l, cfft plan of m, rfft plan of m"""
+        ls = l + il2(l) + 4 + 2 * m + il2(m) + 4 + m + il2(m) + 4
+        ws = np.zeros(ls + 8)
+        ier = I(-1)
+        self.fn("rfft2i_")(ctypes.byref(I(l)), ctypes.byref(I(m)), P(ws), ctypes.byref(I(ls)), ctypes.byref(ier))
+        return ws, ls, ier.value
+
+    def run2r(self, d, ldim, l, m, r, lenwrk_=None, lensav_=None):
+        """rfft2f_/rfft2b_ on a real column-major r(ldim, m).  The reference uses r itself as the complex pass's
+        scratch (fftpack.c:13407), so rows l..ldim-1 come back clobbered there: compare rows < l only."""
+        ws, ls, ier0 = self.init2r(l, m)
+        assert ier0 == 0
+        y = np.array(r, dtype=np.float64, copy=True)
+        lw = (l + 1) * m if lenwrk_ is None else lenwrk_
+        wk = np.zeros(8)
+        if self.prefix == "orc_" or self.lib is ref():
+            wk = np.zeros(max(lw, (l + 2) * m) + 8)
+        ier = I(-1)
+        self.fn("rfft2" + d + "_")(ctypes.byref(I(ldim)), ctypes.byref(I(l)), ctypes.byref(I(m)), P(y), P(ws),
+                                   ctypes.byref(I(ls if lensav_ is None else lensav_)), P(wk), ctypes.byref(I(lw)),
+                                   ctypes.byref(ier))
+        return y, ier.value
+
+
+def rows2(a, ldim, l, m):
+    """the addressed part r(0:l, 0:m) of a column-major array with leading dimension ldim"""
+    a = np.asarray(a)
+    full = np.zeros(ldim * m, a.dtype)
+    full[: min(len(a), ldim * m)] = a[: ldim * m]
+    return full.reshape(m, ldim)[:, :l]
+
+
 def rand_input(fam, count, seed):
     rng = np.random.default_rng(seed)
     if fam == "cfft":

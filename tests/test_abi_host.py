@@ -104,6 +104,21 @@ def test_cfft2_ier_codes():
         assert ier == 3 and np.array_equal(y, c)
 
 
+def test_rfft2_init_and_ier_codes():
+    for (l, m) in ((8, 6), (7, 5), (1, 4), (32, 32)):
+        a, ls, ia = PROD.init2r(l, m)
+        b, _, ib = ORC.init2r(l, m)
+        assert ia == ib == 0 and np.array_equal(a, b)
+    assert np.array_equal(PROD.init2r(8, 6)[0][: len(G["wsave_rfft2_8x6"])], G["wsave_rfft2_8x6"])
+    r = fl.rand_input("rfft", 11 * 6, 4)
+    for d in "fb":
+        for kw, want in ((dict(lenwrk_=9 * 6 - 1), 3), (dict(lensav_=8 + 3 + 4 + 12 + 2 + 4 + 6 + 2 + 4 - 1), 2)):
+            y, ier = PROD.run2r(d, 8, 8, 6, r, **kw)
+            assert ier == want == ORC.run2r(d, 8, 8, 6, r, **kw)[1] and np.array_equal(y, r)
+        y, ier = PROD.run2r(d, 7, 8, 6, r)  # ldim < l
+        assert ier == 5 and np.array_equal(y, r)
+
+
 def test_length_one_is_a_no_op():
     for fam in fl.FAMILIES:
         x = fl.rand_input(fam, 1, 5)

@@ -77,6 +77,11 @@ def test_golden_batched_and_2d():
             ldim = 11 if name.endswith("ld11") else 8
             y, ier = PROD.run2(d, ldim, 8, 6, G[name + "/x"])
             assert ier == 0 and fl.rel_l2(y, G[key]) <= fl.tol(48), name
+        elif name.startswith("rfft2_"):
+            d, (l, m), ldim = name.split("_")[1], (int(v) for v in name.split("_")[2].split("x")), int(name.split("ld")[1])
+            y, ier = PROD.run2r(d, ldim, l, m, G[name + "/x"])
+            assert ier == 0
+            assert fl.rel_l2(fl.rows2(y, ldim, l, m), fl.rows2(G[key], ldim, l, m)) <= fl.tol(l * m), name
         elif name[4:6] == "m_":
             fam, d = name[:4], name[6]
             lot, n = (int(v) for v in name.split("_")[2].split("x"))
@@ -138,6 +143,35 @@ def test_cfft2_vs_oracle():
             b, ib = ORC.run2(d, ldim, l, m, c)
             assert ia == ib == 0
             assert fl.rel_l2(a, b) <= fl.tol(l * m), (d, ldim, l, m, fl.rel_l2(a, b))
+
+
+def test_rfft2_vs_oracle_and_numpy():
+    """2-D real transforms (fftpack.c:13282, :13113) incl. odd sizes, ldim > l, and a size whose rows leave the chip"""
+    for (ldim, l, m) in ((1, 1, 4), (4, 4, 1), (2, 2, 2), (3, 3, 3), (8, 8, 6), (11, 8, 6), (9, 7, 5), (64, 64, 48),
+                         (33, 30, 21), (130, 128, 96), (100, 100, 75), (1024, 1024, 512), (1001, 999, 1000)):
+        r = fl.rand_input("rfft", ldim * (m - 1) + l, 3 * l + m)
+        for d in "fb":
+            a, ia = PROD.run2r(d, ldim, l, m, r)
+            b, ib = ORC.run2r(d, ldim, l, m, r)
+            assert ia == ib == 0
+            e = fl.rel_l2(fl.rows2(a, ldim, l, m), fl.rows2(b, ldim, l, m))
+            assert e <= fl.tol(l * m), (d, ldim, l, m, e)
+        if ldim > l:
+            pad = np.ones(len(r), bool)
+            for j in range(m):
+                pad[j * ldim: j * ldim + l] = False
+            assert np.array_equal(a[pad], r[pad])
+    # definition: F(i, j) half-complex along i of fft2(x) / (l m); then the round trip
+    l, m = 2048, 1536
+    x = fl.rand_input("rfft", l * m, 77)
+    f, ier = PROD.run2r("f", l, l, m, x)
+    assert ier == 0
+    X = np.fft.rfft2(x.reshape(m, l), axes=(0, 1)) / (l * m)  # X[j, f]: rfft along i (fast axis), fft along j
+    F = f.reshape(m, l)
+    k = np.arange(1, l // 2)
+    assert fl.rel_l2(F[:, 2 * k - 1] + 1j * F[:, 2 * k], X[:, k]) <= fl.tol(l * m)
+    g, ier = PROD.run2r("b", l, l, m, f)
+    assert ier == 0 and fl.rel_l2(g, x) <= fl.tol(l * m)
 
 
 def test_known_answers():

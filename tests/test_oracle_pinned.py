@@ -113,6 +113,11 @@ def test_oracle_batched_and_2d_vs_golden():
             ldim = 11 if name.endswith("ld11") else 8
             y, ier = ORC.run2(d, ldim, 8, 6, G[name + "/x"])
             assert ier == 0 and np.array_equal(y, G[key]), name
+        elif name.startswith("rfft2_"):
+            d, (l, m), ldim = name.split("_")[1], (int(v) for v in name.split("_")[2].split("x")), int(name.split("ld")[1])
+            y, ier = ORC.run2r(d, ldim, l, m, G[name + "/x"])
+            assert ier == 0
+            assert fl.rel_l2(fl.rows2(y, ldim, l, m), fl.rows2(G[key], ldim, l, m)) <= 2e-15, name
         elif name[4:6] == "m_":
             fam, d = name[:4], name[6]
             lot, n = (int(v) for v in name.split("_")[2].split("x"))
@@ -140,6 +145,27 @@ def test_oracle_vs_live_reference():
                     assert np.array_equal(a, b), (fam, d, n)
                 else:
                     assert fl.rel_l2(b, a) <= 2e-14 + fl.ref_noise(fam, n), (fam, d, n, fl.rel_l2(b, a))
+
+
+@pytest.mark.skipif(fl.ref() is None, reason="oracle/_ref not built (no /root/reference on this box)")
+def test_oracle_rfft2_vs_live_reference():
+    R = fl.Lib(fl.ref())
+    a, _, _ = R.init2r(12, 10)
+    b, _, _ = ORC.init2r(12, 10)
+    assert np.array_equal(a, b)
+    for (ld, l, m) in ((1, 1, 1), (1, 1, 4), (4, 4, 1), (2, 2, 2), (3, 3, 3), (5, 5, 8), (16, 16, 16), (33, 30, 21), (100, 100, 60)):
+        x = fl.rand_input("rfft", ld * m, l * 100 + m)
+        for d in "fb":
+            ya, ia = R.run2r(d, ld, l, m, x)
+            yb, ib = ORC.run2r(d, ld, l, m, x)
+            assert ia == ib == 0
+            assert fl.rel_l2(fl.rows2(yb, ld, l, m), fl.rows2(ya, ld, l, m)) <= 2e-15, (d, ld, l, m)
+        for kw in (dict(lenwrk_=(l + 1) * m - 1), dict(lensav_=10)):
+            ya, ia = R.run2r("f", ld, l, m, x, **kw)
+            yb, ib = ORC.run2r("f", ld, l, m, x, **kw)
+            assert ia == ib != 0 and np.array_equal(ya, yb)
+    x = fl.rand_input("rfft", 40, 3)
+    assert R.run2r("f", 4, 5, 8, x)[1] == ORC.run2r("f", 4, 5, 8, x)[1] == 5
 
 
 def test_reference_is_the_noisy_side_for_large_primes():
