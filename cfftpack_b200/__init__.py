@@ -91,3 +91,23 @@ class Plan:
             ctypes.c_void_p(ptr), ctypes.byref(_I(lenx)), self._wp, ctypes.byref(_I(self.lensav)),
             ctypes.byref(self._dummy), ctypes.byref(_I(min(lw, 2**31 - 1))), ctypes.byref(ier))
         return ier.value
+
+
+def option_convolution(n, S, K, sigma, theta, kappa, t, r, call=True, black_scholes=False):
+    """Value a batch of options by frequency-domain convolution: the reference's test/vargamma.c:42-106
+    (conv_bsvg_option) for all options in one device-resident pipeline (cfb200_option_convolution).
+    Scalars broadcast against arrays.  Returns (values, N) with N the grid size actually used."""
+    import numpy as np
+    cols = np.broadcast_arrays(*(np.asarray(v, dtype=np.float64) for v in (S, K, sigma, theta, kappa, t, r)),
+                               np.asarray(call, dtype=bool), np.asarray(black_scholes, dtype=bool))
+    lot = max(1, cols[0].size)
+    flat = [np.ascontiguousarray(c.reshape(-1), dtype=np.float64) for c in cols[:7]]
+    flags = np.ascontiguousarray(cols[7].reshape(-1).astype(np.int32) | (cols[8].reshape(-1).astype(np.int32) << 1))
+    values = np.zeros(lot)
+    ier = _I(-1)
+    vp = ctypes.c_void_p
+    N = lib.cfb200_option_convolution(_I(lot), _I(n), *(vp(c.ctypes.data) for c in flat), vp(flags.ctypes.data),
+                                      vp(values.ctypes.data), ctypes.byref(ier))
+    if ier.value != 0:
+        raise RuntimeError(f"cfb200_option_convolution: ier={ier.value} ({last_error()})")
+    return values.reshape(cols[0].shape), N

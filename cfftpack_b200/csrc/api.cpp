@@ -510,6 +510,28 @@ CFB_DEF_REAL(sint, K_SINT)
 CFB_DEF_REAL(cosq, K_COSQ)
 CFB_DEF_REAL(sinq, K_SINQ)
 
+/* test/vargamma.c:42-106 for `lot` options at once; see include/cfftpack_b200.h */
+int cfb200_option_convolution(int lot, int n, const double *S, const double *K, const double *sigma, const double *theta,
+                              const double *kappa, const double *t, const double *r, const int *flags, double *value,
+                              int *ier) {
+  *ier = 0;
+  if (lot <= 0 || n <= 0 || !S || !K || !sigma || !theta || !kappa || !t || !r || !flags || !value) {
+    *ier = 1;
+    return 0;
+  }
+  const int N = next_fast_even_size(n);
+  if (!device_ready()) {
+    *ier = -1;
+    return N;
+  }
+  std::vector<double> par((size_t)8 * lot);
+  const double *cols[7] = {S, K, sigma, theta, kappa, t, r};
+  for (int k = 0; k < 7; ++k) memcpy(&par[(size_t)k * lot], cols[k], (size_t)lot * sizeof(double));
+  for (int o = 0; o < lot; ++o) par[(size_t)7 * lot + o] = (double)(flags[o] & 3);
+  if (!run_option_convolution(lot, N, par.data(), value)) *ier = -1;
+  return N;
+}
+
 int cfb200_cfft2_sharded_phase(int phase, int direction, int l, int m, int rank, int nranks, void *local_src,
                                void *const *peer_dst, int *ier) {
   *ier = 0;

@@ -37,6 +37,10 @@ bool run_c2c_2d(int ldim, int l, int m, int dir, void *c);
 bool run_real_2d(int ldim, int l, int m, int dir, double *r);
 bool run_c2c_2d_sharded_phase(int phase, int dir, int l, int m, int rank, int nranks, void *src, void *const *peers);
 
+/* batched option valuation (option.cu): par = host [8][lot] (S K sigma theta kappa t r flags), value = host [lot] */
+int next_fast_even_size(int n);
+bool run_option_convolution(int lot, int N, const double *par_host, double *value_host);
+
 /* largest core length the single-kernel paths take (for tests and docs) */
 int engine_max_c2c();
 int engine_max_real();

@@ -80,6 +80,15 @@ CFB200_DECL_TRIG(cosq)
 CFB200_DECL_TRIG(sinq)
 
 /* ---- extensions (no counterpart in the reference) ---- */
+/* Batched option valuation by frequency-domain convolution -- the reference's test/vargamma.c:42-106
+ * (conv_bsvg_option: payoff grid -> rfft -> characteristic function -> inverse rfft -> V[N/2] e^{-rt}) for `lot`
+ * options in one call, device-resident between the steps.  All arrays are HOST arrays of length lot; flags[o] bit 0:
+ * call (else put), bit 1: Black-Scholes (else variance gamma).  The grid has N = fft_next_fast_even_size(n) points
+ * (cfftextra.c:42-46); N is the return value.  ier: 0, 1 (bad argument), -1 (CUDA failure). */
+int cfb200_option_convolution(int lot, int n, const double *S, const double *K, const double *sigma, const double *theta,
+                              const double *kappa, const double *t, const double *r, const int *flags, double *value,
+                              int *ier);
+
 /* Sharded cfft2f_/cfft2b_: matrix c(l, m) column-major distributed over `nranks` GPUs of one node.
  * phase 1: local_src = this rank's column slab C[m/nranks][l]; every rank's row slab D[m][l/nranks] is given by
  *          peer_dst[r] (peer-mapped device pointers).  The length-l transforms of the slab are computed and each

@@ -874,6 +874,58 @@ ORC_DEF_TRIG(sinq, K_SINQ)
 
 /* ------------------------------------------------------------------ */
 /* O(N^2) definitions with FFTPACK scaling (test/naivepack.c:12-228).   */
+/* ------------------------------------------------------------------ */
+/* Application path: option value by convolution with the risk-neutral density in the frequency
+ * domain, test/vargamma.c:42-106 (conv_bsvg_option) on top of cfftpack.c:446-492 (rfft_forward / rfft_inverse are a
+ * shift of the half-complex vector, so the characteristic function multiplies the pairs (r[2i-1], r[2i]) directly; the
+ * imaginary parts of the products at i = 0 and i = N/2 are dropped by the shift back).  Sizes: cfftextra.c:20-46. */
+#include <complex.h>
+int orc_next_fast_even_size(int n) {
+  if (n <= 2) return 2;
+  if (n & 1) ++n;
+  for (;; n += 2) {
+    int m = n;
+    while (m % 5 == 0) m /= 5;
+    while (m % 3 == 0) m /= 3;
+    while (m % 2 == 0) m /= 2;
+    if (m == 1) return n;
+  }
+}
+static double _Complex option_charfn(double u, double sigma, double theta, double kappa, double t, double drift, int bs) {
+  if (bs) return cexp(-0.5 * sigma * sigma * u * u * t + I * u * t * drift);
+  double _Complex base = 1.0 + sigma * sigma * kappa * u * u / 2.0 - I * theta * kappa * u;
+  return cpow(base, -t / kappa) * cexp(I * drift * u * t);
+}
+double orc_conv_bsvg_option(int n, double S, double K, double sigma, double theta, double kappa, double t, double r,
+                            int is_call, int is_bs) {
+  int N = orc_next_fast_even_size(n), N2 = N / 2, one = 1, ier = 0, i;
+  int lensav = N + il2(N) + 4;
+  double *V = (double *)calloc((size_t)N, sizeof(double)), *ws = (double *)calloc((size_t)lensav, sizeof(double));
+  double *wk = (double *)calloc((size_t)N, sizeof(double));
+  double L = 2 * 10 * sigma * sqrt(t), ds = L / N, du = 2 * M_PI / (ds * N), lS = log(S), value;
+  double drift = is_bs ? r - 0.5 * sigma * sigma : r + (1.0 / kappa) * log(1.0 - sigma * sigma * kappa / 2.0 - theta * kappa);
+  for (i = 0; i < N; ++i) {
+    double e = exp(lS + (N2 - i) * ds);
+    V[i] = is_call ? (e - K > 0.0 ? e - K : 0.0) : (K - e > 0.0 ? K - e : 0.0);
+  }
+  orc_rfft1i_(&N, ws, &lensav, &ier);
+  orc_rfft1f_(&N, &one, V, &N, ws, &lensav, wk, &N, &ier);
+  for (i = 0; i <= N2; ++i) {
+    double _Complex phi = option_charfn(i * du, sigma, theta, kappa, t, drift, is_bs);
+    if (i == 0) V[0] = creal(V[0] * phi);
+    else if (i == N2) V[N - 1] = creal(V[N - 1] * phi);
+    else {
+      double _Complex v = (V[2 * i - 1] + I * V[2 * i]) * phi;
+      V[2 * i - 1] = creal(v);
+      V[2 * i] = cimag(v);
+    }
+  }
+  orc_rfft1b_(&N, &one, V, &N, ws, &lensav, wk, &N, &ier);
+  value = V[N2] * exp(-r * t);
+  free(V); free(ws); free(wk);
+  return value;
+}
+
 static const double PI_ = 3.14159265358979323846;
 void orc_naive_cfft(int n, const cpx *x, cpx *y, int forward) {
   for (int k = 0; k < n; ++k) {

@@ -88,4 +88,8 @@ double orc_lot_parallel(orc_fft1_fn fn, int is_complex, int lot, int n, void *da
 #ifdef __cplusplus
 }
 #endif
+/* test/vargamma.c:42-106, cfftextra.c:42-46 */
+int orc_next_fast_even_size(int n);
+double orc_conv_bsvg_option(int n, double S, double K, double sigma, double theta, double kappa, double t, double r,
+                            int is_call, int is_bs);
 #endif

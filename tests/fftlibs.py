@@ -245,3 +245,32 @@ def ref_noise(fam, n):
     """extra allowance when comparing against the *reference*: its generic-prime real pass builds the
     roots of unity by recurrence (fftpack.c:12784-12805), so its own error grows ~ 4e-15 * prime."""
     return 5e-15 * max_generic_factor(underlying(fam, n)) if fam != "cfft" else 0.0
+
+
+def vargamma_ref():
+    """the reference's test/vargamma.c as a library (oracle/Makefile); None on the GPU box"""
+    return _load(os.path.join(ROOT, "oracle", "_ref", "libvargamma_ref.so"))
+
+
+OPTION_CASES = [  # (S, K, sigma, theta, kappa, t, r, call, black_scholes); first row = test/vargamma.c:108-118
+    (100.0, 98.0, 0.12, -0.14, 0.2, 1.0, 0.05, 1, 1), (100.0, 98.0, 0.12, -0.14, 0.2, 1.0, 0.05, 1, 0),
+    (100.0, 98.0, 0.12, -0.14, 0.2, 1.0, 0.05, 0, 1), (100.0, 98.0, 0.12, -0.14, 0.2, 1.0, 0.05, 0, 0),
+    (90.0, 100.0, 0.2, -0.1, 0.3, 0.5, 0.03, 1, 0), (110.0, 100.0, 0.3, -0.2, 0.1, 2.0, 0.01, 0, 0),
+    (100.0, 105.0, 0.12, -0.14, 0.2, 1.0, 0.05, 1, 1), (100.0, 98.0, 0.25, 0.05, 0.5, 0.25, 0.0, 1, 0),
+]
+
+
+def option_oracle(n, case):
+    lib = oracle()
+    lib.orc_conv_bsvg_option.restype = ctypes.c_double
+    lib.orc_conv_bsvg_option.argtypes = [ctypes.c_int] + [ctypes.c_double] * 7 + [ctypes.c_int] * 2
+    return lib.orc_conv_bsvg_option(n, *case)
+
+
+def option_product(lib, n, cases):
+    cols = [np.ascontiguousarray([c[k] for c in cases], dtype=np.float64) for k in range(7)]
+    flags = np.ascontiguousarray([c[7] | (c[8] << 1) for c in cases], dtype=np.int32)
+    val = np.zeros(len(cases))
+    ier = I(-9)
+    N = lib.cfb200_option_convolution(I(len(cases)), I(n), *(P(c) for c in cols), P(flags), P(val), ctypes.byref(ier))
+    return val, N, ier.value

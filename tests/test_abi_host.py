@@ -119,6 +119,14 @@ def test_rfft2_init_and_ier_codes():
         assert ier == 5 and np.array_equal(y, r)
 
 
+def test_option_convolution_argument_checks():
+    val, N, ier = fl.option_product(fl.product(), 0, fl.OPTION_CASES[:2])
+    assert ier == 1 and not val.any()
+    if not fl.has_gpu():
+        val, N, ier = fl.option_product(fl.product(), 1001, fl.OPTION_CASES[:2])
+        assert (N, ier) == (1024, -1) and not val.any()  # sizes like cfftextra.c:42-46; no CPU path
+
+
 def test_length_one_is_a_no_op():
     for fam in fl.FAMILIES:
         x = fl.rand_input(fam, 1, 5)

@@ -174,6 +174,28 @@ def test_rfft2_vs_oracle_and_numpy():
     assert ier == 0 and fl.rel_l2(g, x) <= fl.tol(l * m)
 
 
+def test_option_convolution_batched_vs_oracle_golden_and_black_scholes():
+    """the reference's option-pricing application, batched on the device"""
+    for n in (128, 1000, 4096, 5000):
+        val, N, ier = fl.option_product(fl.product(), n, fl.OPTION_CASES)
+        assert ier == 0
+        assert np.max(np.abs(val - G[f"option_{n}"]) / np.abs(G[f"option_{n}"])) <= 1e-12, n
+    # a larger batch: every option must equal its single-option oracle value; the grid size leaves the chip at 2^16
+    rng = np.random.default_rng(9)
+    cases = [(float(rng.uniform(80, 120)), float(rng.uniform(80, 120)), float(rng.uniform(0.1, 0.4)), float(rng.uniform(-0.3, 0.1)),
+              float(rng.uniform(0.1, 0.5)), float(rng.uniform(0.2, 2.0)), float(rng.uniform(0.0, 0.06)), int(rng.integers(2)),
+              int(rng.integers(2))) for _ in range(300)]
+    val, N, ier = fl.option_product(fl.product(), 2000, cases)
+    assert ier == 0 and N == 2000
+    want = np.array([fl.option_oracle(2000, c) for c in cases])
+    assert np.max(np.abs(val - want) / np.maximum(np.abs(want), 1e-3)) <= 1e-11
+    val, N, ier = fl.option_product(fl.product(), 1 << 16, fl.OPTION_CASES[:2])
+    assert ier == 0 and abs(val[0] - 8.779874623570) < 2e-8 and abs(val[1] - 9.3424659413582116) < 2e-5
+    import cfftpack_b200 as cb
+    v2, _ = cb.option_convolution(4096, 100.0, np.array([98.0, 105.0]), 0.12, -0.14, 0.2, 1.0, 0.05, call=True, black_scholes=True)
+    assert abs(v2[0] - 8.779878465793) < 1e-9
+
+
 def test_known_answers():
     """impulse, constant and single tone under the reference's scaling (forward 1/N e^{-i}, backward e^{+i})"""
     n = 4096

@@ -168,6 +168,18 @@ def test_oracle_rfft2_vs_live_reference():
     assert R.run2r("f", 4, 5, 8, x)[1] == ORC.run2r("f", 4, 5, 8, x)[1] == 5
 
 
+def test_option_convolution_oracle_vs_golden_and_closed_form():
+    """test/vargamma.c: the oracle's restatement against values produced by the reference itself, and the
+    Black-Scholes closed form the reference prints (8.779874623570; its own N = 4096 value is 8.779878465793)"""
+    assert [fl.oracle().orc_next_fast_even_size(n) for n in (1, 2, 3, 7, 11, 13, 127, 1001, 4097)] == \
+        [2, 2, 4, 8, 12, 16, 128, 1024, 4320]
+    for n in (128, 1000, 4096, 5000):
+        got = np.array([fl.option_oracle(n, c) for c in fl.OPTION_CASES])
+        assert np.max(np.abs(got - G[f"option_{n}"]) / np.abs(G[f"option_{n}"])) <= 1e-13, n
+    assert abs(fl.option_oracle(4096, fl.OPTION_CASES[0]) - 8.779878465793) < 1e-11
+    assert abs(fl.option_oracle(1 << 16, fl.OPTION_CASES[0]) - 8.779874623570) < 2e-8
+
+
 def test_reference_is_the_noisy_side_for_large_primes():
     """rfft 998 = 2*499 (cost N=999): against the long-double definition the oracle is ~100x closer than
     the golden (reference) answer, which justifies fl.ref_noise()."""

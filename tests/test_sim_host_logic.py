@@ -143,6 +143,15 @@ def test_rfft2(libs):
                 assert np.array_equal(a[pad], r[pad])
 
 
+def test_option_convolution_pipeline(libs):
+    """payoff -> rfftmf -> characteristic function -> rfftmb -> value, batched (test/vargamma.c:42-106)"""
+    for n in (128, 1000):
+        val, N, ier = fl.option_product(fl.sim(), n, fl.OPTION_CASES)
+        want = np.array([fl.option_oracle(n, c) for c in fl.OPTION_CASES])
+        assert ier == 0 and N == fl.oracle().orc_next_fast_even_size(n)
+        assert np.max(np.abs(val - want) / np.abs(want)) <= 1e-12
+
+
 def test_pipelined_host_staging(libs):
     """pinned host arrays go through HBM in lot-chunks on three streams; chunk size forced small here"""
     import ctypes

@@ -72,6 +72,25 @@ def case_c1():
         dt = (time.perf_counter() - t0) / reps
         print(f"cfft1f+cfft1b N=1024 round trip, {label}: {dt * 1e6:8.1f} us per round trip (2 calls, via ctypes)", flush=True)
 
+def case_options(n=4096, lot=16384):
+    """batched option valuation (test/vargamma.c) end to end from host parameters to host values,
+    against the oracle's single-option CPU version on one core"""
+    import numpy as np
+    rng = np.random.default_rng(1)
+    K = rng.uniform(80, 120, lot)
+    cb.option_convolution(n, 100.0, K, 0.12, -0.14, 0.2, 1.0, 0.05)  # warm plans and scratch
+    for bs in (True, False):
+        t0 = time.perf_counter()
+        v, N = cb.option_convolution(n, 100.0, K, 0.12, -0.14, 0.2, 1.0, 0.05, call=True, black_scholes=bs)
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        w = np.array([fl.option_oracle(n, (100.0, float(k), 0.12, -0.14, 0.2, 1.0, 0.05, 1, int(bs))) for k in K[:64]])
+        dc = (time.perf_counter() - t1) / 64
+        err = float(np.max(np.abs(v[:64] - w) / np.abs(w)))
+        print(f"option convolution {'BS' if bs else 'VG'} N={N} lot={lot}: {dt * 1e3:8.2f} ms = {lot / dt / 1e3:8.1f} k options/s "
+              f"(CPU oracle, 1 core: {1 / dc / 1e3:6.2f} k options/s; max rel diff {err:.1e})", flush=True)
+
+
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c1", "c2", "c3", "c4", "c5", "misc"]
 if "c1" in which:
     case_c1()
@@ -84,6 +103,8 @@ if "c4" in which:
         case(fam, n, 32768); case(fam, n, 32768, d="b")
 if "c5" in which:
     case2d(16384, 16384); case2d(4096, 4096)
+if "n4" in which:
+    case_options()
 if "misc" in which:
     case("cfft", 1024, 262144); case("cfft", 256, 1048576); case("cfft", 64, 4194304); case("cfft", 8192, 32768)
     case("cfft", 1000, 262144); case("cfft", 4096, 65536, inc=65536, jump=1); case("rfft", 1000, 262144)
