@@ -173,14 +173,7 @@ void scratch_release_all() {
   }
 }
 
-/* a caller array, resolved to device memory */
-struct DeviceView {
-  void *dev = nullptr;
-  void *host = nullptr;
-  size_t bytes = 0;
-  bool staged = false;
-};
-static bool view_open(void *user, size_t bytes, DeviceView &v) {
+bool view_open(void *user, size_t bytes, DeviceView &v) {
   if (!device_ready()) return false;
   cudaPointerAttributes at;
   memset(&at, 0, sizeof(at));
@@ -200,7 +193,7 @@ static bool view_open(void *user, size_t bytes, DeviceView &v) {
   if (!v.dev) return false;
   return cuda_ok(cudaMemcpyAsync(v.dev, user, bytes, cudaMemcpyHostToDevice, t_stream), "cudaMemcpyAsync(H2D)");
 }
-static bool view_close(DeviceView &v, bool ok) {
+bool view_close(DeviceView &v, bool ok) {
   if (!v.staged) return ok;
   if (ok) ok = cuda_ok(cudaMemcpyAsync(v.host, v.dev, v.bytes, cudaMemcpyDeviceToHost, t_stream), "cudaMemcpyAsync(D2H)");
   bool s = cuda_ok(cudaStreamSynchronize(t_stream), "cudaStreamSynchronize");
@@ -394,6 +387,8 @@ static int real_1d(int kind, int *n, int *inc, double *x, int *lenx, int *lensav
   if (*lenx < span1(*n, *inc)) *ier = 1;
   else if (*lensav < fam_lensav(kind, *n)) *ier = 2;
   else if (*lenwrk < fam_lenwrk(kind, *n, 1, false)) *ier = 3;
+  // sinq1b_ falls through its checks into cosq1b_ and reports that failure as 20 (fftpack.c:14151-14179)
+  if (*ier && kind == K_SINQ && dir > 0 && *n > 1) *ier = 20;
   if (*ier || *n == 1) return 0;
   DeviceView v;
   bool ok = view_open(x, (size_t)span1(*n, *inc) * 8, v);
@@ -410,6 +405,7 @@ static int real_multi(int kind, int *lot, int *jump, int *n, int *inc, double *x
   else if (*lensav < fam_lensav(kind, *n)) *ier = 2;
   else if ((long long)*lenwrk < fam_lenwrk(kind, *n, *lot, true)) *ier = 3;
   else if (!strides_consistent(*inc, *jump, *n, *lot)) *ier = 4;
+  if (*ier && kind == K_SINQ && dir > 0 && *n > 1) *ier = 20;  // sinqmb_, same fall-through
   if (*ier || *n == 1) return 0;
   const int nn = *n, ii = *inc, jj = *jump;
   bool ok = run_on_array(x, 8, *lot, jj, nn, ii,

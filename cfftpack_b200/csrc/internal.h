@@ -29,6 +29,17 @@ int sm_count();
 void *scratch_get(int slot, size_t bytes);
 void scratch_release_all();
 
+/* a caller array, resolved to device memory: device pointers pass through, host arrays are staged (scratch slot 1)
+ * on the current stream and copied back + synchronised by view_close */
+struct DeviceView {
+  void *dev = nullptr;
+  void *host = nullptr;
+  size_t bytes = 0;
+  bool staged = false;
+};
+bool view_open(void *user, size_t bytes, DeviceView &v);
+bool view_close(DeviceView &v, bool ok);
+
 /* ---- transform drivers (dispatch.cu).  Pointers are DEVICE pointers; strides in elements. ---- */
 bool run_c2c(int n, long long lot, long long inc, long long jump, int dir, void *c);
 bool run_c2c_scaled(int n, long long lot, long long inc, long long jump, int dir, void *c, double scale);

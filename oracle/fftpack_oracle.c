@@ -835,6 +835,8 @@ static int trig_1(int kind, int *n, int *inc, double *x, int *lenx, double *wsav
   if (*lenx < *inc * (*n - 1) + 1) *ier = 1;
   else if (*lensav < trig_lensav(kind, *n)) *ier = 2;
   else if (*lenwrk < trig_lenwrk1(kind, *n)) *ier = 3;
+  /* sinq1b_ falls through its argument checks into cosq1b_, whose failure it reports as 20 (fftpack.c:14151-14179) */
+  if (*ier && kind == K_SINQ && !fwd && *n > 1) *ier = 20;
   if (*ier) return 0;
   /* private scratch: the oracle's generic real passes need n+1 extra doubles */
   double *scratch = (double *)malloc(sizeof(double) * (size_t)(3 * *n + 8));
@@ -848,6 +850,7 @@ static int trig_m(int kind, int *lot, int *jump, int *n, int *inc, double *x, in
   else if (*lensav < trig_lensav(kind, *n)) *ier = 2;
   else if (*lenwrk < trig_lenwrkm(kind, *n, *lot)) *ier = 3;
   else if (!orc_xercon(*inc, *jump, *n, *lot)) *ier = 4;
+  if (*ier && kind == K_SINQ && !fwd && *n > 1) *ier = 20;  /* sinqmb_ :14319-14409, same fall-through as sinq1b_ */
   if (*ier) return 0;
   double *scratch = (double *)malloc(sizeof(double) * (size_t)(3 * *n + 8));
   /* the batched drivers (mcstf1_ :7150, msntf1_ :10636, mcsqf1_ :6839) are
@@ -924,6 +927,155 @@ double orc_conv_bsvg_option(int n, double S, double K, double sigma, double thet
   value = V[N2] * exp(-r * t);
   free(V); free(ws); free(wk);
   return value;
+}
+
+/* ------------------------------------------------------------------ */
+/* L2 object wrapper, cfftpack/cfftpack.c: one handle per (algorithm, n), the reference's scaling
+ * conventions with and without fft_ortho.  algo numbers follow cfftintern.h's enum (CFFT 1, RFFT 2, CFFT2 3, DCT1 4,
+ * DCT 5, DST1 7, DST 8).  Quirks kept on purpose: the length passed down is n (n*inc only for DCT, :186/:203), so a
+ * stride > 1 yields ier = 1 everywhere else; the ortho factors of fft_forward/inverse are 1/sqrt(n) and sqrt(n) ON
+ * TOP of FFTPACK's 1/n (:69-76, :90-97); ortho loops ignore the stride except in dct_forward/inverse. */
+struct orc_l2 {
+  int algo, n, m, ortho, inc, lensav, lenwork;
+  double *save, *work;
+};
+void orc_l2_free(orc_l2_t *f) {
+  if (!f) return;
+  free(f->save);
+  free(f->work);
+  free(f);
+}
+orc_l2_t *orc_l2_create(int algo, int n, int m) {
+  orc_l2_t *f;
+  int ier = 0;
+  if (n <= 0 || (algo == 3 && m <= 0) || (algo == 4 && n <= 1)) return NULL;
+  f = (orc_l2_t *)calloc(1, sizeof(*f));
+  f->algo = algo; f->n = n; f->m = m; f->inc = 1;
+  switch (algo) {
+    case 1: f->lensav = 2 * n + il2(n) + 4; f->lenwork = 2 * n; break;                          /* :8-29 */
+    case 2: f->lensav = n + il2(n) + 4; f->lenwork = n; break;                                  /* :427-444 */
+    case 3: f->lensav = 2 * n + il2(n) + 2 * m + il2(m) + 8; f->lenwork = 2 * n * m; break;     /* :102-127 */
+    case 7: f->lensav = n / 2 + n + il2(n) + 4; f->lenwork = 2 * n + 2; break;                  /* :374-392 */
+    default: f->lensav = 2 * n + il2(n) + 4; f->lenwork = n; break;                             /* :155, :223, :302 */
+  }
+  f->save = (double *)calloc((size_t)f->lensav + 8, sizeof(double));
+  f->work = (double *)calloc((size_t)f->lenwork + 8, sizeof(double));
+  switch (algo) {
+    case 1: orc_cfft1i_(&n, f->save, &f->lensav, &ier); break;
+    case 2: orc_rfft1i_(&n, f->save, &f->lensav, &ier); break;
+    case 3: orc_cfft2i_(&n, &m, f->save, &f->lensav, &ier); break;
+    case 4: orc_cost1i_(&n, f->save, &f->lensav, &ier); break;
+    case 5: orc_cosq1i_(&n, f->save, &f->lensav, &ier); break;
+    case 7: orc_sint1i_(&n, f->save, &f->lensav, &ier); break;
+    case 8: orc_sinq1i_(&n, f->save, &f->lensav, &ier); break;
+    default: ier = 1;
+  }
+  if (ier) { orc_l2_free(f); return NULL; }
+  return f;
+}
+void orc_l2_ortho(orc_l2_t *f, int ortho) { if (f) f->ortho = ortho; }
+void orc_l2_stride(orc_l2_t *f, int stride) { if (f) f->inc = stride > 0 ? stride : 1; }
+static void scale_first_rest(double *x, int n, int inc, double first, double rest) {
+  int i;
+  x[0] *= first;
+  for (i = 1; i < n; ++i) x[(long)i * inc] *= rest;
+}
+/* cfftpack.c:245-275: both directions of the orthonormal DCT-I go through the unscaled backward transform */
+static int l2_dct1_ortho(orc_l2_t *f, double *x) {
+  const double r2 = 1.0 / sqrt(2.0), m = sqrt(2.0 / (f->n - 1.0));
+  double ev = (x[0] + x[f->n - 1]) * (-1.0 + r2), od = (x[0] - x[f->n - 1]) * (-1.0 + r2);
+  int ier = 0, i;
+  orc_cost1b_(&f->n, &f->inc, x, &f->n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+  if (ier) return ier;
+  for (i = 0; i < f->n; ++i) x[i] = (x[i] + (i % 2 == 0 ? ev : od)) * m;
+  x[0] *= r2;
+  x[f->n - 1] *= r2;
+  return 0;
+}
+static int l2_run(orc_l2_t *f, void *data, int fwd) {
+  int ier = 0, n, len, i;
+  double *x = (double *)data;
+  if (!f || !data) return -1;
+  n = f->n;
+  switch (f->algo) {
+    case 1: {  /* fft_forward :57-78, fft_inverse :81-99 */
+      cpx *c = (cpx *)data;
+      double mul = fwd ? 1.0 / sqrt(n) : sqrt(n);
+      if (fwd) orc_cfft1f_(&n, &f->inc, c, &n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+      else orc_cfft1b_(&n, &f->inc, c, &n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+      if (ier) return ier;
+      if (f->ortho) for (i = 0; i < n; ++i) { c[i].r *= mul; c[i].i *= mul; }
+      return 0;
+    }
+    case 3:  /* fft2_forward :131-141, fft2_inverse :143-152: ldim = l */
+      if (fwd) orc_cfft2f_(&n, &n, &f->m, (cpx *)data, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+      else orc_cfft2b_(&n, &n, &f->m, (cpx *)data, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+      return ier;
+    case 5:  /* dct_forward :176-195 (DCT-III), dct_inverse :198-218 (DCT-II) */
+      len = n * f->inc;
+      if (fwd) {
+        if (f->ortho) scale_first_rest(x, n, f->inc, sqrt(n), sqrt(0.5 * n));
+        orc_cosq1f_(&n, &f->inc, x, &len, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+      } else {
+        orc_cosq1b_(&n, &f->inc, x, &len, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+        if (f->ortho) scale_first_rest(x, n, f->inc, 1.0 / sqrt(n), sqrt(2.0 / n));
+      }
+      return ier;
+    case 4:  /* dct1_forward :277-292, dct1_inverse :294-308 */
+      if (f->ortho) return l2_dct1_ortho(f, x);
+      if (fwd) orc_cost1f_(&n, &f->inc, x, &n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+      else orc_cost1b_(&n, &f->inc, x, &n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+      return ier;
+    case 8:  /* dst_forward :330-352, dst_inverse :354-371 */
+      if (fwd) {
+        if (f->ortho) scale_first_rest(x, n, 1, sqrt(1.0 / n), sqrt(0.5 / n));
+        orc_sinq1f_(&n, &f->inc, x, &n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+        if (f->ortho) for (i = 0; i < n; ++i) x[i] *= (double)n;
+        return ier;
+      }
+      orc_sinq1b_(&n, &f->inc, x, &n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+      if (ier) return ier;
+      if (f->ortho) scale_first_rest(x, n, 1, sqrt(1.0 / n), sqrt(2.0 / n));
+      return 0;
+    case 7:  /* dst1_forward :394-408 (ortho: same as inverse), dst1_inverse :410-426 */
+      if (fwd && !f->ortho) {
+        orc_sint1f_(&n, &f->inc, x, &n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+        return ier;
+      }
+      orc_sint1b_(&n, &f->inc, x, &n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+      if (ier) return ier;
+      if (f->ortho) for (i = 0; i < n; ++i) x[i] *= sqrt(2.0 / (n + 1));
+      return 0;
+    default: return -2;
+  }
+}
+int orc_l2_forward(orc_l2_t *f, void *data) { return l2_run(f, data, 1); }
+int orc_l2_inverse(orc_l2_t *f, void *data) { return l2_run(f, data, 0); }
+/* rfft_forward :446-469: half-complex vector shifted by one slot into complex[n/2+1] with zero imaginary ends */
+int orc_l2_rfft_forward(orc_l2_t *f, const double *in, void *out) {
+  double *d = (double *)out;
+  int ier = 0, one = 1, i, n;
+  if (!f || !in || !out) return -1;
+  if (f->algo != 2) return -2;
+  n = f->n;
+  if (in != d) memcpy(d, in, (size_t)n * sizeof(double));
+  orc_rfft1f_(&n, &one, d, &n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+  for (i = n; i > 1; --i) d[i] = d[i - 1];
+  d[1] = 0;
+  if (n % 2 == 0) d[n + 1] = 0;
+  return ier;
+}
+/* rfft_inverse :471-490 */
+int orc_l2_rfft_inverse(orc_l2_t *f, const void *in, double *out) {
+  const double *d = (const double *)in;
+  int ier = 0, one = 1, i, n;
+  if (!f || !in || !out) return -1;
+  if (f->algo != 2) return -2;
+  n = f->n;
+  out[0] = d[0];
+  for (i = 1; i < n; ++i) out[i] = d[i + 1];
+  orc_rfft1b_(&n, &one, out, &n, f->save, &f->lensav, f->work, &f->lenwork, &ier);
+  return ier;
 }
 
 static const double PI_ = 3.14159265358979323846;

@@ -92,4 +92,14 @@ double orc_lot_parallel(orc_fft1_fn fn, int is_complex, int lot, int n, void *da
 int orc_next_fast_even_size(int n);
 double orc_conv_bsvg_option(int n, double S, double K, double sigma, double theta, double kappa, double t, double r,
                             int is_call, int is_bs);
+/* cfftpack/cfftpack.c (L2 object wrapper); algo numbers as in cfftintern.h */
+typedef struct orc_l2 orc_l2_t;
+orc_l2_t *orc_l2_create(int algo, int n, int m);
+void orc_l2_free(orc_l2_t *f);
+void orc_l2_ortho(orc_l2_t *f, int ortho);
+void orc_l2_stride(orc_l2_t *f, int stride);
+int orc_l2_forward(orc_l2_t *f, void *data);
+int orc_l2_inverse(orc_l2_t *f, void *data);
+int orc_l2_rfft_forward(orc_l2_t *f, const double *in, void *out);
+int orc_l2_rfft_inverse(orc_l2_t *f, const void *in, double *out);
 #endif

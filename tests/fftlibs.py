@@ -274,3 +274,108 @@ def option_product(lib, n, cases):
     ier = I(-9)
     N = lib.cfb200_option_convolution(I(len(cases)), I(n), *(P(c) for c in cols), P(flags), P(val), ctypes.byref(ier))
     return val, N, ier.value
+
+
+L2_ALGOS = {"fft": 1, "dct1": 4, "dct": 5, "dst1": 7, "dst": 8}  # cfftintern.h numbering (the oracle's orc_l2_create)
+
+
+def bind_l2(lib):
+    """argtypes for the reference's object API (cfftpack/cfftpack.h) as exported by `lib`"""
+    vp = ctypes.c_void_p
+    for name in ("fft_create", "rfft_create", "dct_create", "dct1_create", "dst_create", "dst1_create"):
+        getattr(lib, name).restype, getattr(lib, name).argtypes = vp, [ctypes.c_int]
+    lib.fft2_create.restype, lib.fft2_create.argtypes = vp, [ctypes.c_int] * 2
+    for fam in ("fft", "fft2", "dct", "dct1", "dst", "dst1"):
+        for d in ("forward", "inverse"):
+            getattr(lib, f"{fam}_{d}").argtypes = [vp, vp]
+    lib.fft_ortho.argtypes, lib.fft_stride.argtypes, lib.fft_free.argtypes = [vp, ctypes.c_bool], [vp, ctypes.c_int], [vp]
+    lib.rfft_forward.argtypes = lib.rfft_inverse.argtypes = [vp, vp, vp]
+    if hasattr(lib, "cfb200_fft_batch"):
+        lib.cfb200_fft_batch.argtypes = [vp, ctypes.c_int]
+    return lib
+
+
+def bind_l2_oracle():
+    lib, vp = oracle(), ctypes.c_void_p
+    lib.orc_l2_create.restype, lib.orc_l2_create.argtypes = vp, [ctypes.c_int] * 3
+    lib.orc_l2_forward.argtypes = lib.orc_l2_inverse.argtypes = [vp, vp]
+    lib.orc_l2_ortho.argtypes = lib.orc_l2_stride.argtypes = [vp, ctypes.c_int]
+    lib.orc_l2_free.argtypes = [vp]
+    lib.orc_l2_rfft_forward.argtypes = lib.orc_l2_rfft_inverse.argtypes = [vp, vp, vp]
+    return lib
+
+
+L2_FAMILY = {"fft": "cfft", "dct": "cosq", "dct1": "cost", "dst": "sinq", "dst1": "sint"}
+
+
+def l2_compare(lib, sizes, exact_codes=True, tol_=1e-13, noise=False):
+    """`lib` (reference names) against the oracle's restatement of cfftpack.c: every family, both directions, with and
+    without fft_ortho, stride 1 and 2 (the latter is an error upstream for all but the DCT); rfft repack; fft2."""
+    S, O = bind_l2(lib), bind_l2_oracle()
+    worst = 0.0
+    for n in sizes:
+        for nm, algo in L2_ALGOS.items():
+            for ortho in (0, 1):
+                for inc in (1, 2):
+                    fs, fo = getattr(S, nm + "_create")(n), O.orc_l2_create(algo, n, 0)
+                    assert (fs is None) == (fo is None), (nm, n)
+                    if fs is None:
+                        continue
+                    S.fft_ortho(fs, bool(ortho)); O.orc_l2_ortho(fo, ortho)
+                    S.fft_stride(fs, inc); O.orc_l2_stride(fo, inc)
+                    x = np.random.default_rng(n + algo).uniform(-1, 1, n * inc * (2 if algo == 1 else 1))
+                    for d in ("forward", "inverse"):
+                        a, b = x.copy(), x.copy()
+                        ra, rb = getattr(S, f"{nm}_{d}")(fs, P(a)), getattr(O, "orc_l2_" + d)(fo, P(b))
+                        if exact_codes:
+                            assert ra == rb, (nm, n, ortho, inc, d, ra, rb)
+                        else:
+                            assert (ra == 0) == (rb == 0), (nm, n, ortho, inc, d, ra, rb)
+                        if ra == 0:
+                            e = rel_l2(a, b)
+                            assert e <= tol_ + (ref_noise(L2_FAMILY[nm], n) if noise else 0.0), (nm, n, ortho, inc, d, e)
+                            worst = max(worst, e)
+                    S.fft_free(fs); O.orc_l2_free(fo)
+        fs, fo = S.rfft_create(n), O.orc_l2_create(2, n, 0)
+        x = np.random.default_rng(n).uniform(-1, 1, n)
+        a, b = np.full(n + 3, 7.0), np.full(n + 3, 7.0)
+        assert S.rfft_forward(fs, P(x), P(a)) == O.orc_l2_rfft_forward(fo, P(x), P(b)) == 0
+        used = n + 2 if n % 2 == 0 else n + 1
+        assert rel_l2(a[:used], b[:used]) <= tol_ and np.array_equal(a[used:], b[used:]), n
+        ya, yb = np.zeros(n), np.zeros(n)
+        assert S.rfft_inverse(fs, P(a), P(ya)) == O.orc_l2_rfft_inverse(fo, P(b), P(yb)) == 0
+        assert rel_l2(ya, yb) <= tol_ and rel_l2(ya, x) <= tol_, n
+        S.fft_free(fs); O.orc_l2_free(fo)
+    fs, fo = S.fft2_create(8, 6), O.orc_l2_create(3, 8, 6)
+    c = np.random.default_rng(1).uniform(-1, 1, 96)
+    for d in ("forward", "inverse"):
+        a, b = c.copy(), c.copy()
+        assert getattr(S, "fft2_" + d)(fs, P(a)) == getattr(O, "orc_l2_" + d)(fo, P(b)) == 0 and rel_l2(a, b) <= tol_
+    S.fft_free(fs); O.orc_l2_free(fo)
+    return worst
+
+
+def l2_batch_check(lib, n=60, lot=5):
+    """cfb200_fft_batch: lot sequences back to back == the same handle called per sequence"""
+    S = bind_l2(lib)
+    for nm, algo in L2_ALGOS.items():
+        w = n * (2 if algo == 1 else 1)
+        f = getattr(S, nm + "_create")(n)
+        S.fft_ortho(f, True)
+        x = np.random.default_rng(3).uniform(-1, 1, w * lot)
+        a = x.copy()
+        for o in range(lot):
+            seg = a[o * w:(o + 1) * w].copy()
+            assert getattr(S, nm + "_forward")(f, P(seg)) == 0
+            a[o * w:(o + 1) * w] = seg
+        S.cfb200_fft_batch(f, lot)
+        b = x.copy()
+        assert getattr(S, nm + "_forward")(f, P(b)) == 0 and rel_l2(a, b) <= 1e-14, nm
+        S.fft_free(f)
+    f = S.rfft_create(n)
+    S.cfb200_fft_batch(f, lot)
+    x = np.random.default_rng(4).uniform(-1, 1, n * lot)
+    out, back = np.zeros(lot * (n + 2)), np.zeros(n * lot)
+    assert S.rfft_forward(f, P(x), P(out)) == 0 and S.rfft_inverse(f, P(out), P(back)) == 0
+    assert rel_l2(back, x) <= 1e-14
+    S.fft_free(f)

@@ -90,7 +90,8 @@ def test_ier_codes_match_oracle(fam):
         big = fl.rand_input(fam, 200, 3)
         a, ia = PROD.runm(fam, d, 4, 2, 6, 3, big)
         b, ib = ORC.runm(fam, d, 4, 2, 6, 3, big)
-        assert ia == ib == 4, (fam, d, ia, ib)
+        # sinqmb_ reports every argument error as 20 (upstream fall-through, fftpack.c:14151-14179)
+        assert ia == ib == (20 if (fam, d) == ("sinq", "b") else 4), (fam, d, ia, ib)
     ws, ier = PROD.init(fam, n, lensav_override=fl.lensav(fam, n) - 1)
     assert ier == 2
 

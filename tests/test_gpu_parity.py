@@ -196,6 +196,31 @@ def test_option_convolution_batched_vs_oracle_golden_and_black_scholes():
     assert abs(v2[0] - 8.779878465793) < 1e-9
 
 
+def test_l2_object_api_vs_oracle():
+    """fft_create/.../rfft_inverse (cfftpack.h) on the device, incl. orthonormal scalings, the rfft
+    repack, return codes, the batch extension, and device-resident data"""
+    fl.l2_compare(fl.product(), (1, 2, 3, 4, 5, 8, 16, 30, 31, 60, 100, 1000, 1001, 4096))
+    fl.l2_batch_check(fl.product())
+    fl.l2_batch_check(fl.product(), n=1000, lot=64)
+    torch = _torch()
+    S = fl.bind_l2(fl.product())
+    n, lot = 4096, 256
+    x = torch.rand(lot * n, device="cuda", dtype=torch.float64) - 0.5
+    out = torch.zeros(lot * (n + 2), device="cuda", dtype=torch.float64)
+    back = torch.zeros_like(x)
+    f = S.rfft_create(n)
+    S.cfb200_fft_batch(f, lot)
+    assert S.rfft_forward(f, x.data_ptr(), out.data_ptr()) == 0 and S.rfft_inverse(f, out.data_ptr(), back.data_ptr()) == 0
+    fl.product().cfb200_synchronize()
+    X = torch.fft.rfft(x.view(lot, n), dim=1) / n * 2
+    got = torch.view_as_complex(out.view(lot, n // 2 + 1, 2))
+    # FFTPACK's half-complex convention: (2/n) Re, -(2/n) Im for 0 < k < n/2; (1/n) at the ends
+    assert float((got[:, 1:n // 2] - torch.conj(X[:, 1:n // 2])).abs().max()) < 1e-13
+    assert float((got[:, 0].real - X[:, 0].real / 2).abs().max()) < 1e-13
+    assert float((back - x).abs().max()) < 1e-13
+    S.fft_free(f)
+
+
 def test_known_answers():
     """impulse, constant and single tone under the reference's scaling (forward 1/N e^{-i}, backward e^{+i})"""
     n = 4096

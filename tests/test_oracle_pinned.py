@@ -180,6 +180,30 @@ def test_option_convolution_oracle_vs_golden_and_closed_form():
     assert abs(fl.option_oracle(1 << 16, fl.OPTION_CASES[0]) - 8.779874623570) < 2e-8
 
 
+@pytest.mark.skipif(fl.ref() is None, reason="oracle/_ref not built (no /root/reference on this box)")
+def test_oracle_ier_codes_vs_live_reference():
+    """every argument-error code, incl. the upstream quirk that sinq1b_/sinqmb_ report 20 (fftpack.c:14151-14179)"""
+    R = fl.Lib(fl.ref())
+    n, lot = 12, 3
+    for fam in fl.FAMILIES:
+        xm, x1, big = fl.rand_input(fam, n * lot, 1), fl.rand_input(fam, n, 1), fl.rand_input(fam, 200, 3)
+        for d in "fb":
+            for kw in (dict(lenx=n * lot - 1), dict(lensav_=fl.lensav(fam, n) - 1), dict(lenwrk_=fl.lenwrk(fam, n, lot) - 1)):
+                assert R.runm(fam, d, lot, n, n, 1, xm, **kw)[1] == ORC.runm(fam, d, lot, n, n, 1, xm, **kw)[1] != 0, (fam, d, kw)
+            for kw in (dict(lenx=n - 1), dict(lensav_=fl.lensav(fam, n) - 1), dict(lenwrk_=fl.lenwrk(fam, n) - 1)):
+                assert R.run1(fam, d, n, x1, **kw)[1] == ORC.run1(fam, d, n, x1, **kw)[1] != 0, (fam, d, kw)
+            assert R.runm(fam, d, 4, 2, 6, 3, big)[1] == ORC.runm(fam, d, 4, 2, 6, 3, big)[1] != 0, (fam, d)
+
+
+@pytest.mark.skipif(fl.naive_ref() is None, reason="oracle/_ref not built (no /root/reference on this box)")
+def test_oracle_l2_wrapper_vs_live_reference():
+    """the oracle's restatement of cfftpack.c (orc_l2_*) against the reference's own object API, all families,
+    ortho on/off, stride errors, rfft repack, fft2.  Return codes are compared as zero/non-zero only: with a bad
+    stride the reference keeps transforming and reports whichever inner code it meets last."""
+    worst = fl.l2_compare(fl.naive_ref(), (1, 2, 3, 4, 5, 8, 16, 30, 31, 60, 100, 1000, 1001), exact_codes=False, tol_=2e-14, noise=True)
+    print("L2 oracle vs reference, worst rel-L2", worst)
+
+
 def test_reference_is_the_noisy_side_for_large_primes():
     """rfft 998 = 2*499 (cost N=999): against the long-double definition the oracle is ~100x closer than
     the golden (reference) answer, which justifies fl.ref_noise()."""

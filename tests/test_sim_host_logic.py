@@ -152,6 +152,12 @@ def test_option_convolution_pipeline(libs):
         assert np.max(np.abs(val - want) / np.abs(want)) <= 1e-12
 
 
+def test_l2_object_api(libs):
+    """include/cfftpack_b200_l2.h: the reference's fft_t API served by the library, vs the oracle's cfftpack.c"""
+    fl.l2_compare(fl.sim(), (1, 2, 3, 4, 5, 8, 16, 30, 31, 60, 100, 1000, 1001))
+    fl.l2_batch_check(fl.sim())
+
+
 def test_pipelined_host_staging(libs):
     """pinned host arrays go through HBM in lot-chunks on three streams; chunk size forced small here"""
     import ctypes
