@@ -173,6 +173,29 @@ void scratch_release_all() {
   }
 }
 
+/* Short host arrays (a single cfft1f_ of a few thousand points: config 1) skip the two copy-engine launches: the data
+ * is placed in a per-thread pinned, device-mapped bounce buffer that the kernels read and write across PCIe directly. */
+static const size_t BOUNCE_BYTES = 64 << 10;
+struct Bounce {
+  void *p = nullptr;
+  bool tried = false;
+  ~Bounce() {
+    if (p) cudaFreeHost(p);
+  }
+};
+static thread_local Bounce t_bounce;
+static void *bounce_get() {
+  if (!t_bounce.tried) {
+    t_bounce.tried = true;
+    static const bool off = getenv("CFB200_NO_BOUNCE") != nullptr;
+    if (off || cudaHostAlloc(&t_bounce.p, BOUNCE_BYTES, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      t_bounce.p = nullptr;
+    }
+  }
+  return t_bounce.p;
+}
+
 bool view_open(void *user, size_t bytes, DeviceView &v) {
   if (!device_ready()) return false;
   cudaPointerAttributes at;
@@ -189,12 +212,23 @@ bool view_open(void *user, size_t bytes, DeviceView &v) {
   }
   v.host = user;
   v.staged = true;
+  if (bytes <= BOUNCE_BYTES && bounce_get()) {
+    v.mapped = true;
+    v.dev = t_bounce.p;  // unified addressing: the mapped buffer has the same address on the device
+    memcpy(v.dev, user, bytes);
+    return true;
+  }
   v.dev = scratch_get(1, bytes);
   if (!v.dev) return false;
   return cuda_ok(cudaMemcpyAsync(v.dev, user, bytes, cudaMemcpyHostToDevice, t_stream), "cudaMemcpyAsync(H2D)");
 }
 bool view_close(DeviceView &v, bool ok) {
   if (!v.staged) return ok;
+  if (v.mapped) {
+    bool s = cuda_ok(cudaStreamSynchronize(t_stream), "cudaStreamSynchronize");
+    if (ok && s) memcpy(v.host, v.dev, v.bytes);
+    return ok && s;
+  }
   if (ok) ok = cuda_ok(cudaMemcpyAsync(v.host, v.dev, v.bytes, cudaMemcpyDeviceToHost, t_stream), "cudaMemcpyAsync(D2H)");
   bool s = cuda_ok(cudaStreamSynchronize(t_stream), "cudaStreamSynchronize");
   return ok && s;

@@ -36,6 +36,7 @@ struct DeviceView {
   void *host = nullptr;
   size_t bytes = 0;
   bool staged = false;
+  bool mapped = false;  // short host array placed in the pinned, device-mapped bounce buffer
 };
 bool view_open(void *user, size_t bytes, DeviceView &v);
 bool view_close(DeviceView &v, bool ok);

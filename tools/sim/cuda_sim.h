@@ -114,6 +114,8 @@ static inline cudaError_t cudaFree(void *p) {
 }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFreeHost(void *p) { return cudaFree(p); }
+enum { cudaHostAllocPortable = 1, cudaHostAllocMapped = 2 };
+static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = 0) {
   memmove(d, s, n);
   return 0;
