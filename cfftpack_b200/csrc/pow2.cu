@@ -149,6 +149,57 @@ bool launch_r2c_stream(long long lot, long long jump, double *r) {
   return cuda_ok(cudaGetLastError(), "pow2_r2c_stream_kernel launch");
 }
 
+/* half-length real kernel: stage tables of the length-M transform followed by w_N^t, t = 0..NT */
+template <class C>
+const cpx *pow2_half_table() {
+  typedef StreamSmem<C> S;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  int l2 = 0;
+  while ((1 << l2) < C::N) ++l2;
+  auto key = std::make_tuple(dev, l2, C::LP, 200);
+  auto it = g_tw.find(key);
+  if (it != g_tw.end()) return it->second;
+  std::vector<cpx> h((size_t)S::TWS_COUNT + HalfSmem<C>::WT);
+  size_t o = 0;
+  for (int st = 0; st < C::NFULL; ++st) {
+    if (C::stage_last(st)) continue;
+    const int m = C::stage_m(st);
+    const long long ncur = (long long)m * C::P;
+    for (int e = 1; e <= 4; e += 3)
+      for (int p = 0; p < m; ++p) {
+        unit_root((long long)p * e, ncur, &h[o].x, &h[o].y);
+        ++o;
+      }
+  }
+  for (int t = 0; t <= C::NT; ++t, ++o) unit_root(t, 2LL * C::N, &h[o].x, &h[o].y);
+  cpx *d = nullptr;
+  if (!cuda_ok(cudaMalloc((void **)&d, h.size() * sizeof(cpx)), "cudaMalloc(pow2 twiddles)")) return nullptr;
+  if (!cuda_ok(cudaMemcpy(d, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy(pow2 twiddles)")) {
+    cudaFree(d);
+    return nullptr;
+  }
+  g_tw[key] = d;
+  return d;
+}
+
+template <int LOG2N, int THREADS, int DIR>
+bool launch_r2c_half(long long lot, long long jump, double *r) {
+  typedef Pow2Cfg<LOG2N - 1, 4, 1, THREADS> C;
+  constexpr int MINB = (HalfSmem<C>::BYTES > 110 * 1024) ? 1 : (HalfSmem<C>::BYTES > 56 * 1024 ? 2 : (THREADS <= 128 ? 4 : 2));
+  const cpx *tw = pow2_half_table<C>();
+  if (!tw) return false;
+  auto kern = pow2_r2c_half_kernel<C, MINB, DIR>;
+  if (!set_smem_once(kern, HalfSmem<C>::BYTES)) return false;
+  const long long ntiles = (lot + C::TPB - 1) / C::TPB;
+  const long long cap = (long long)MINB * sm_count();
+  const long long grid = ntiles < cap ? ntiles : cap;
+  CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, HalfSmem<C>::BYTES, current_stream(), r, lot, jump, tw, ntiles);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "pow2_r2c_half_kernel launch");
+}
+
 /* tuning knob for experiments (N = 4096 only): CFB200_POW2_VARIANT, see DESIGN.md */
 int variant() {
   static int v = -1;
@@ -184,6 +235,13 @@ bool launch_r2c(long long lot, long long jump, double *r) {
   const bool tma_ok = (jump % 2 == 0) && (((uintptr_t)r & 15) == 0);
   if (!tma_ok || (LOG2N == 12 && variant() == 1))
     return launch_r2c_cfg<Pow2Cfg<LOG2N>, (LOG2N >= 13 ? 1 : 2), DIR>(lot, jump, r);
+  if (LOG2N == 12) {
+    // experiment: CFB200_R2C_HALF=1|2 selects the half-length single-row kernel with 256 / 128 threads per
+    // CTA.  Measured 1.00 / 0.86 ms against 0.82 ms for the pair kernel at N = 4096, lot = 65536, so it is off by default.
+    static const int half = getenv("CFB200_R2C_HALF") ? atoi(getenv("CFB200_R2C_HALF")) : 0;
+    if (half == 1) return launch_r2c_half<12, 256, DIR>(lot, jump, r);
+    if (half == 2) return launch_r2c_half<12, 128, DIR>(lot, jump, r);
+  }
   return launch_r2c_stream<Pow2Cfg<LOG2N>, StreamMinB<LOG2N>::value, DIR>(lot, jump, r);
 }
 

@@ -158,6 +158,20 @@ def test_l2_object_api(libs):
     fl.l2_batch_check(fl.sim())
 
 
+def test_half_length_real_kernel_experiment():
+    """CFB200_R2C_HALF selects the single-row half-length kernel; env is read once per process"""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import fftlibs as fl; "
+            "S = fl.Lib(fl.sim()); O = fl.Lib(fl.oracle(), 'orc_'); "
+            "x = fl.rand_input('rfft', 3 * 4102, 5); "
+            "r = [fl.rel_l2(S.runm('rfft', d, 3, 4102, 4096, 1, x)[0], O.runm('rfft', d, 3, 4102, 4096, 1, x)[0]) for d in 'fb']; "
+            "assert max(r) < 1e-14, r" % os.path.dirname(os.path.abspath(__file__)))
+    for v in ("1", "2"):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CFB200_R2C_HALF=v), capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr[-2000:]
+
+
 def test_pipelined_host_staging(libs):
     """pinned host arrays go through HBM in lot-chunks on three streams; chunk size forced small here"""
     import ctypes
