@@ -267,9 +267,9 @@ bool launch_tile_stream(TileParams &P) {
 }
 
 /* TMA tensor-box variant: rows contiguous on the input side (jump_lo = 1), tiles never straddle an inner batch group */
-template <int LOG2N, int DIR, bool STAGED>
+template <int LOG2N, int DIR, bool STAGED, int THREADS = 256>
 bool launch_tile_tma(TileParams &P) {
-  typedef Pow2Cfg<LOG2N, 4, 1> C;
+  typedef Pow2Cfg<LOG2N, 4, 1, THREADS> C;
   P.tw = pow2_stream_table<C>();
   if (!P.tw) return false;
   auto kern = pow2_tile_tma_kernel<C, DIR, STAGED>;
@@ -284,7 +284,8 @@ bool launch_tile_tma(TileParams &P) {
     return false;
   const long long ntiles = (P.lot + C::TPB - 1) / C::TPB;
   long long per_sm = (long long)((SMEM_LIMIT + 1024) / (smem + 1024));
-  if (per_sm > 2) per_sm = 2;
+  const long long reg_cap = C::THREADS <= 128 ? 4 : 2;
+  if (per_sm > reg_cap) per_sm = reg_cap;
   if (per_sm < 1) per_sm = 1;
   long long grid = per_sm * sm_count();
   if (grid > ntiles) grid = ntiles;
@@ -302,9 +303,14 @@ bool launch_tile(TileParams &P) {
     const bool layout_ok = !P.in_staged && P.ain.jump_lo == 1 && P.ain.nlo % C::TPB == 0 && P.lot % P.ain.nlo == 0 &&
                            (((uintptr_t)P.in) & 15) == 0 && P.ain.inc > 0 && P.ain.jump_hi >= 0 &&
                            (unsigned long long)P.ain.inc * 16 < (1ULL << 40) && (unsigned long long)P.ain.jump_hi * 16 < (1ULL << 40);
+    static const int small_cta = getenv("CFB200_TILE_THREADS") ? atoi(getenv("CFB200_TILE_THREADS")) == 128 : 0;
+    typedef Pow2Cfg<LOG2N, 4, 1, 128> C1;
+    const bool layout1_ok = layout_ok && P.ain.nlo % C1::TPB == 0;
+    if (!no_tma && small_cta && LOG2N <= 8 && box_ok && layout1_ok) return launch_tile_tma<(LOG2N <= 8 ? LOG2N : 8), DIR, false, 128>(P);
     if (!no_tma && box_ok && layout_ok && TileTmaSmem<C, false>::bytes(P.fs_count) <= SMEM_LIMIT)
       return launch_tile_tma<LOG2N, DIR, false>(P);
     const bool rows_ok = P.in_staged && P.ain.inc == 1 && (((uintptr_t)P.in) & 15) == 0;
+    if (!no_tma && small_cta && LOG2N <= 8 && rows_ok) return launch_tile_tma<(LOG2N <= 8 ? LOG2N : 8), DIR, true, 128>(P);
     if (!no_tma && rows_ok && TileTmaSmem<C, true>::bytes(P.fs_count) <= SMEM_LIMIT) return launch_tile_tma<LOG2N, DIR, true>(P);
   }
   static const bool direct = getenv("CFB200_TILE_DIRECT") != nullptr;

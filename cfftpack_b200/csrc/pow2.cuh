@@ -868,7 +868,7 @@ struct TileTmaSmem {
 };
 
 template <class C, int DIR, bool STAGED>
-__global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_tma_kernel(const TileParams P, const CFB_GRID_CONSTANT TensorMap3 tmap,
+__global__ void __launch_bounds__(C::THREADS, (C::THREADS <= 128 ? 4 : 2)) pow2_tile_tma_kernel(const TileParams P, const CFB_GRID_CONSTANT TensorMap3 tmap,
                                                                       long long ntiles) {
   CFB_DYN_SMEM(smem_raw);
   typedef TileTmaSmem<C, STAGED> TS;

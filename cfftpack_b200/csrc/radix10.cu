@@ -53,7 +53,8 @@ template <int K>
 long long grid_for(long long ntiles) {
   typedef R10Cfg<K> C;
   long long per_sm = (long long)((SMEM_LIMIT + 1024) / (C::BYTES + 1024));
-  if (per_sm > 3) per_sm = 3;
+  const long long reg_cap = C::THREADS <= 128 ? 5 : 3;
+  if (per_sm > reg_cap) per_sm = reg_cap;
   if (per_sm < 1) per_sm = 1;
   const long long cap = per_sm * sm_count();
   return ntiles < cap ? ntiles : cap;
@@ -94,7 +95,7 @@ bool r10_cost_launch(long long npairs, int dir, double *x, const double *trig) {
   if (!tw) return false;
   const long long ntiles = (npairs + C::TPB - 1) / C::TPB;
   long long per_sm = (long long)((SMEM_LIMIT + 1024) / (R10Cost::BYTES + 1024));
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > C::MINB) per_sm = C::MINB;
   long long grid = per_sm * sm_count();
   if (grid > ntiles) grid = ntiles;
   if (dir < 0) {

@@ -12,6 +12,10 @@
 #define CFB_RADIX10_CUH
 #include "pow2.cuh"
 
+#ifndef CFB_R10_THREADS
+#define CFB_R10_THREADS 128  // one sequence per CTA, 4-5 CTAs per SM: measured 3-11% faster than 256 (two per CTA)
+#endif
+
 namespace cfb {
 
 /* 10-point DFT in registers: two 5-point DFTs (even / odd inputs) and a radix-2 level with the 10th roots */
@@ -62,7 +66,8 @@ struct R10Cfg {
   static constexpr int N = (K == 2) ? 100 : 1000;
   static constexpr int NT = N / P;                       // working threads per sequence
   static constexpr int NTP = (NT <= 16) ? 16 : 128;      // threads reserved per sequence (padded)
-  static constexpr int THREADS = 256;
+  static constexpr int THREADS = (NTP > CFB_R10_THREADS) ? NTP : CFB_R10_THREADS;
+  static constexpr int MINB = THREADS <= 128 ? 4 : 2;    // CTAs per SM the register budget is cut for
   static constexpr int TPB = THREADS / NTP;              // sequences (pairs) per CTA
   static constexpr int XT = N + 4 * (N / P);             // exchange row: 4 pad doubles per 10 (14-double pitch: rows stay
                                                          // 16-byte aligned and the 16-byte stores of stage 0 conflict-free)
@@ -133,7 +138,7 @@ __device__ __forceinline__ void r10_core(cpx (&a)[10], double *__restrict__ xr, 
 }
 
 template <int K, int DIR>
-__global__ void __launch_bounds__(256, 2) r10_c2c_stream_kernel(cpx *__restrict__ c, long long lot, long long jump,
+__global__ void __launch_bounds__(R10Cfg<K>::THREADS, R10Cfg<K>::MINB) r10_c2c_stream_kernel(cpx *__restrict__ c, long long lot, long long jump,
                                                                 const cpx *__restrict__ tw, double scale, long long ntiles) {
   typedef R10Cfg<K> C;
   CFB_DYN_SMEM(smem_raw);
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(256, 2) r10_c2c_stream_kernel(cpx *__restrict_
  * (fftpack.c:5693-5738, :5604-5652) fused into the register load and the store (trig[i] = cos((i+1) pi / 2n) in
  * shared memory).  DIR = -1 forward, +1 backward (user-level direction). */
 template <int K, int KIND, int DIR>
-__global__ void __launch_bounds__(256, 2) r10_r2c_stream_kernel(double *__restrict__ r, long long lot, long long jump,
+__global__ void __launch_bounds__(R10Cfg<K>::THREADS, R10Cfg<K>::MINB) r10_r2c_stream_kernel(double *__restrict__ r, long long lot, long long jump,
                                                                 const cpx *__restrict__ tw, const double *__restrict__ trig_g,
                                                                 long long ntiles) {
   typedef R10Cfg<K> C;
@@ -382,7 +387,7 @@ struct R10Cost {
 };
 
 template <int DIR>
-__global__ void __launch_bounds__(256, 2) r10_cost_stream_kernel(double *__restrict__ r, long long npairs,
+__global__ void __launch_bounds__(R10Cfg<3>::THREADS, R10Cfg<3>::MINB) r10_cost_stream_kernel(double *__restrict__ r, long long npairs,
                                                                  const cpx *__restrict__ tw, const double *__restrict__ trig_g,
                                                                  long long ntiles) {
   typedef R10Cfg<3> C;
