@@ -65,58 +65,79 @@ __device__ __forceinline__ void pass_fixed(const cpx *__restrict__ src, cpx *__r
   }
 }
 
-/* generic odd radix r (the reference's c1fgkf_/c1fgkb_, fftpack.c:1650/:1410): each thread produces the
- * output pair (k, r-k) of one butterfly from the symmetric sums, O(r) work per output */
+/* generic odd radix r (the reference's c1fgkf_/c1fgkb_, fftpack.c:1650/:1410): O(r) work per output from the symmetric
+ * sums.  A work item is one butterfly x a block of CFB_GENERIC_KB output pairs (k, r-k): the inputs a_j, a_{r-j} are
+ * read from shared memory once per block instead of once per pair, which is what bounds this pass for large r. */
 template <int DIR, bool PAD>
 __device__ __forceinline__ void pass_generic(const cpx *__restrict__ src, cpx *__restrict__ dst, int T, int ldz, int M,
                                              const PassDesc &pd, const cpx *__restrict__ tw, int tid, int nthr, int ps) {
+  constexpr int KB = CFB_GENERIC_KB;
   const int r = pd.radix, nb = M / r, s = pd.s, m = pd.m, half = (r + 1) / 2;
-  const int per = nb * half;  // work items per sequence: (k in [0, half)) x butterflies, butterflies fastest
+  const int per = nb * (1 + (half - 1 + KB - 1) / KB);  // items per sequence: (k = 0 | k-blocks) x butterflies, butterflies fastest
   const int total = per * T;
   const cpx *twp = tw + pd.twoff;
   const cpx *rt = tw + pd.rtoff;
   for (int idx = tid; idx < total; idx += nthr) {
     int t = fast_div(idx, per, pd.mag_per), rem = idx - t * per;
-    int k = fast_div(rem, nb, pd.mag_nb), b = rem - k * nb;
+    int kb = fast_div(rem, nb, pd.mag_nb), b = rem - kb * nb;
     int p = fast_div(b, s, pd.mag_s), q = b - p * s;
     const cpx *sp = src + t * ldz;
     cpx *dp = dst + t * ldz;
     const int o0 = q + s * r * p;
     cpx a0 = sp[padq<PAD>(b, ps)];
-    if (k == 0) {
+    if (kb == 0) {
       cpx acc = a0;
       for (int j = 1; j < r; ++j) acc = cadd(acc, sp[padq<PAD>(b + j * nb, ps)]);
       dp[padq<PAD>(o0, ps)] = acc;
     } else {
       // X_k = a0 + sum_{j=1}^{half-1} [ c_jk (a_j + a_{r-j}) + DIR*i * s_jk (a_j - a_{r-j}) ],  X_{r-k}: minus sign
-      double ar = a0.x, ai = a0.y, br = 0.0, bi = 0.0;
-      int jk = 0;
+      const int k0 = 1 + KB * (kb - 1);
+      double ar[KB], ai[KB], br[KB], bi[KB];
+      int kk[KB], jk[KB];
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        kk[c] = k0 + c < half ? k0 + c : half - 1;  // the tail block recomputes its last pair (not stored twice)
+        jk[c] = 0;
+        ar[c] = a0.x;
+        ai[c] = a0.y;
+        br[c] = 0.0;
+        bi[c] = 0.0;
+      }
       for (int j = 1; j < half; ++j) {
-        jk += k;
-        if (jk >= r) jk -= r;
-        cpx w = rt[jk];  // (cos, -sin)(2 pi jk / r)
-        cpx u = sp[padq<PAD>(b + j * nb, ps)], v = sp[padq<PAD>(b + (r - j) * nb, ps)];
-        double pr = u.x + v.x, pi = u.y + v.y, mr = u.x - v.x, mi = u.y - v.y;
-        ar = fma(w.x, pr, ar);
-        ai = fma(w.x, pi, ai);
-        br = fma(-w.y, mr, br);  // sin * (a_j - a_{r-j})
-        bi = fma(-w.y, mi, bi);
+        const cpx u = sp[padq<PAD>(b + j * nb, ps)], v = sp[padq<PAD>(b + (r - j) * nb, ps)];
+        const double pr = u.x + v.x, pi = u.y + v.y, mr = u.x - v.x, mi = u.y - v.y;
+#pragma unroll
+        for (int c = 0; c < KB; ++c) {
+          jk[c] += kk[c];
+          if (jk[c] >= r) jk[c] -= r;
+          const cpx w = rt[jk[c]];  // (cos, -sin)(2 pi jk / r)
+          ar[c] = fma(w.x, pr, ar[c]);
+          ai[c] = fma(w.x, pi, ai[c]);
+          br[c] = fma(-w.y, mr, br[c]);  // sin * (a_j - a_{r-j})
+          bi[c] = fma(-w.y, mi, bi[c]);
+        }
       }
-      // DIR*i*(br + i bi) = DIR*(-bi + i br)
-      cpx xk, xc;
-      if (DIR < 0) {
-        xk = make_double2(ar + bi, ai - br);
-        xc = make_double2(ar - bi, ai + br);
-      } else {
-        xk = make_double2(ar - bi, ai + br);
-        xc = make_double2(ar + bi, ai - br);
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        const int k = k0 + c;
+        if (k < half) {
+          // DIR*i*(br + i bi) = DIR*(-bi + i br)
+          cpx xk, xc;
+          if (DIR < 0) {
+            xk = make_double2(ar[c] + bi[c], ai[c] - br[c]);
+            xc = make_double2(ar[c] - bi[c], ai[c] + br[c]);
+          } else {
+            xk = make_double2(ar[c] - bi[c], ai[c] + br[c]);
+            xc = make_double2(ar[c] + bi[c], ai[c] - br[c]);
+          }
+          if (m > 1) {
+            xk = ctw<DIR>(xk, twp[(k - 1) * m + p]);
+            xc = ctw<DIR>(xc, twp[(r - k - 1) * m + p]);
+          }
+          dp[padq<PAD>(o0 + k * s, ps)] = xk;
+          dp[padq<PAD>(o0 + (r - k) * s, ps)] = xc;
+        }
       }
-      if (m > 1) {
-        xk = ctw<DIR>(xk, twp[(k - 1) * m + p]);
-        xc = ctw<DIR>(xc, twp[(r - k - 1) * m + p]);
-      }
-      dp[padq<PAD>(o0 + k * s, ps)] = xk;
-      dp[padq<PAD>(o0 + (r - k) * s, ps)] = xc;
     }
   }
 }

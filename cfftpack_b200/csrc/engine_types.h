@@ -12,6 +12,10 @@ enum Kind { K_C2C = 0, K_RFFT = 1, K_COST = 2, K_SINT = 3, K_COSQ = 4, K_SINQ = 
 #define CFB_MAXPASS 24
 #define CFB_ENGINE_THREADS 256
 
+/* generic odd radix: output pairs (k, r-k) one thread computes together from each pair of inputs it loads */
+#define CFB_GENERIC_KB 4
+static inline int generic_items(int r) { return 1 + ((r + 1) / 2 - 1 + CFB_GENERIC_KB - 1) / CFB_GENERIC_KB; }
+
 struct PassDesc {
   int radix;  // 2,3,4,5,8 or a generic odd prime
   int s;      // product of the radices of earlier passes
@@ -20,7 +24,7 @@ struct PassDesc {
   int rtoff;  // generic radix only: offset of the table exp(-2 pi i j / radix), j < radix
   unsigned mag_s;   // ceil(2^32 / s):  b / s == __umulhi(b, mag_s) for b * s < 2^32 (s > 1)
   unsigned mag_nb;  // ceil(2^32 / nb), nb = M / radix butterflies per sequence
-  unsigned mag_per; // generic radix: ceil(2^32 / (nb * (radix + 1) / 2))
+  unsigned mag_per; // generic radix: ceil(2^32 / (nb * generic_items(radix)))
 };
 
 /* element (g, e) of a batch lives at  (g / nlo) * jump_hi + (g % nlo) * jump_lo + e * inc  (units: elements) */

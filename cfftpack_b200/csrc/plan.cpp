@@ -155,7 +155,7 @@ const CorePlan *get_core_plan(int M) {
       const long long nb = M / r;
       pd.mag_s = magic(s);
       pd.mag_nb = magic(nb);
-      pd.mag_per = magic(nb * ((r + 1) / 2));
+      pd.mag_per = magic(nb * generic_items(r));
     }
     if (m > 1)
       for (int kk = 1; kk < r; ++kk)
