@@ -217,8 +217,18 @@ def run_cfft2(args, torch, dist, cb, rank, local_rank, world, barrier):
     ms = float(t.item())
     hbm_bytes = 2 * 2 * 16 * l * m  # two read+write passes minimum
     link_bytes = 2 * 16 * l * m * (world - 1) // (world * world)  # per GPU, both exchanges
+    roofline = None
+    if world == 1:  # dominant kernel: the four-step sweep (pow2_tile_tma_kernel), 4 launches per transform, each one
+        peak, src = hbm_peak()  # one read + one write of the whole array per sweep
+        sweep = 2 * 16 * l * m
+        ach = sweep / (ms / 4 * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": 8544292864 if l == 16384 else None, "peak_source": src,
+                    "kernel": "pow2_tile_tma_kernel (4 sweeps per cfft2f_)", "algorithmic_bytes_per_launch": sweep,
+                    "avg_launch_ms": ms / 4, "traffic_source": "profiles/r1_ncu_tile_tma_v1.txt"}
     if rank == 0:
         print(json.dumps({
+            "roofline": roofline,
             "metric": f"cfft2f FP64 {l}x{m} algorithmic HBM GB/s (2-pass minimum)", "value": hbm_bytes / (ms * 1e-3) / 1e9,
             "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 2), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -349,7 +359,7 @@ def main():
         nbytes = lot * n * esz * 8
         e2e = {"value": world * bytes_rank / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-               "note": "host pinned array -> cfftmf_ C ABI -> host; copies inside the timed region"}
+               "note": f"host pinned array -> {fam}mf_ C ABI -> host; copies inside the timed region"}
         del h
     except Exception as ex:  # report, never hide
         e2e = {"value": None, "unit": "GB/s", "error": str(ex)}
