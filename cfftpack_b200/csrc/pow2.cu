@@ -268,7 +268,7 @@ bool launch_tile_stream(TileParams &P) {
 
 /* TMA tensor-box variant: rows contiguous on the input side (jump_lo = 1), tiles never straddle an inner batch group */
 template <int LOG2N, int DIR, bool STAGED, int THREADS = 256>
-bool launch_tile_tma(TileParams &P) {
+bool launch_tile_tma(TileParams &P, bool *declined) {  // *declined: the tensor map could not be built, use another kernel
   typedef Pow2Cfg<LOG2N, 4, 1, THREADS> C;
   P.tw = pow2_stream_table<C>();
   if (!P.tw) return false;
@@ -280,8 +280,10 @@ bool launch_tile_tma(TileParams &P) {
   const unsigned long long nlo = (unsigned long long)P.ain.nlo;
   const unsigned long long nhi = (unsigned long long)((P.lot + P.ain.nlo - 1) / P.ain.nlo);
   if (!STAGED && !make_tensor_map3(&tm, P.in, 2 * nlo, (unsigned long long)C::N, nhi, (unsigned long long)P.ain.inc * 16,
-                        (unsigned long long)(P.ain.jump_hi ? P.ain.jump_hi : 1) * 16, 2 * C::TPB, C::N))
+                        (unsigned long long)(P.ain.jump_hi ? P.ain.jump_hi : 1) * 16, 2 * C::TPB, C::N)) {
+    *declined = true;
     return false;
+  }
   const long long ntiles = (P.lot + C::TPB - 1) / C::TPB;
   long long per_sm = (long long)((SMEM_LIMIT + 1024) / (smem + 1024));
   const long long reg_cap = C::THREADS <= 128 ? 4 : 2;
@@ -299,6 +301,7 @@ bool launch_tile(TileParams &P) {
   {
     typedef Pow2Cfg<LOG2N, 4, 1> C;
     static const bool no_tma = getenv("CFB200_TILE_NO_TMA") != nullptr;
+    bool declined = false, ok = false;
     const bool box_ok = C::N <= 256 && 2 * C::TPB <= 256;
     const bool layout_ok = !P.in_staged && P.ain.jump_lo == 1 && P.ain.nlo % C::TPB == 0 && P.lot % P.ain.nlo == 0 &&
                            (((uintptr_t)P.in) & 15) == 0 && P.ain.inc > 0 && P.ain.jump_hi >= 0 &&
@@ -306,12 +309,17 @@ bool launch_tile(TileParams &P) {
     static const int small_cta = getenv("CFB200_TILE_THREADS") ? atoi(getenv("CFB200_TILE_THREADS")) == 128 : 0;
     typedef Pow2Cfg<LOG2N, 4, 1, 128> C1;
     const bool layout1_ok = layout_ok && P.ain.nlo % C1::TPB == 0;
-    if (!no_tma && small_cta && LOG2N <= 8 && box_ok && layout1_ok) return launch_tile_tma<(LOG2N <= 8 ? LOG2N : 8), DIR, false, 128>(P);
-    if (!no_tma && box_ok && layout_ok && TileTmaSmem<C, false>::bytes(P.fs_count) <= SMEM_LIMIT)
-      return launch_tile_tma<LOG2N, DIR, false>(P);
+    if (!no_tma && small_cta && LOG2N <= 8 && box_ok && layout1_ok) {
+      ok = launch_tile_tma<(LOG2N <= 8 ? LOG2N : 8), DIR, false, 128>(P, &declined);
+      if (!declined) return ok;
+    }
+    if (!no_tma && box_ok && layout_ok && TileTmaSmem<C, false>::bytes(P.fs_count) <= SMEM_LIMIT) {
+      ok = launch_tile_tma<LOG2N, DIR, false>(P, &declined);
+      if (!declined) return ok;
+    }
     const bool rows_ok = P.in_staged && P.ain.inc == 1 && (((uintptr_t)P.in) & 15) == 0;
-    if (!no_tma && small_cta && LOG2N <= 8 && rows_ok) return launch_tile_tma<(LOG2N <= 8 ? LOG2N : 8), DIR, true, 128>(P);
-    if (!no_tma && rows_ok && TileTmaSmem<C, true>::bytes(P.fs_count) <= SMEM_LIMIT) return launch_tile_tma<LOG2N, DIR, true>(P);
+    if (!no_tma && small_cta && LOG2N <= 8 && rows_ok) return launch_tile_tma<(LOG2N <= 8 ? LOG2N : 8), DIR, true, 128>(P, &declined);
+    if (!no_tma && rows_ok && TileTmaSmem<C, true>::bytes(P.fs_count) <= SMEM_LIMIT) return launch_tile_tma<LOG2N, DIR, true>(P, &declined);
   }
   static const bool direct = getenv("CFB200_TILE_DIRECT") != nullptr;
   static const bool wide = getenv("CFB200_TILE_WIDE") != nullptr;  // experiment: 512-thread CTAs, twice the rows per tile
