@@ -429,22 +429,32 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
       // next lane by shuffle, so that all but the warp-edge lanes issue full 16-byte stores.
       const double sc = 1.0 / (double)N;
       const int lane = tid & 31;
+      // three passes over the 8 slots so that the shared-memory loads, the arithmetic and the shuffles of different
+      // slots overlap (one fused loop exposed each latency 8 times: 39 % of the stall samples, profiles/r1_ncu_r2c_src.txt).
+      // The upper half of a[] is free after the exchange: it receives the partners, then the results of row b.
 #pragma unroll
       for (int i = 0; i < P / 2; ++i) {
         const int f = t + NT * i;
-        cpx u = a[i], v = zq[f == 0 ? 0 : N / 2 - f];
-        double Aa, Ba, Ab, Bb;
-        if (f == 0) {  // slot 0 holds X0 itself
-          Aa = 0.0;
-          Ab = 0.0;
-          Ba = u.x * sc;
-          Bb = u.y * sc;
+        a[P / 2 + i] = zq[f == 0 ? 0 : N / 2 - f];
+      }
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        const int f = t + NT * i;
+        const cpx u = a[i], v = a[P / 2 + i];
+        if (f == 0) {  // slot 0 holds X0 itself; A_{N/2} = X_{N/2} / N closes the row
+          if (va) xa[N - 1] = v.x * sc;
+          if (vb) xb[N - 1] = v.y * sc;
+          a[i] = make_double2(0.0, u.x * sc);
+          a[P / 2 + i] = make_double2(0.0, u.y * sc);
         } else {
-          Aa = (u.x + v.x) * sc;
-          Ba = (v.y - u.y) * sc;
-          Ab = (u.y + v.y) * sc;
-          Bb = (u.x - v.x) * sc;
+          a[i] = make_double2((u.x + v.x) * sc, (v.y - u.y) * sc);          // (A, B) of row a
+          a[P / 2 + i] = make_double2((u.y + v.y) * sc, (u.x - v.x) * sc);  // (A, B) of row b
         }
+      }
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        const int f = t + NT * i;
+        const double Aa = a[i].x, Ba = a[i].y, Ab = a[P / 2 + i].x, Bb = a[P / 2 + i].y;
         const double Aa_n = __shfl_down_sync(0xffffffffu, Aa, 1), Ab_n = __shfl_down_sync(0xffffffffu, Ab, 1);
         if (lane < 31 && t != NT - 1) {
           if (va) *(double2 *)(xa + 2 * f) = make_double2(Ba, Aa_n);
@@ -456,10 +466,6 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
         if ((lane == 0 || t == 0) && f != 0) {
           if (va) xa[2 * f - 1] = Aa;
           if (vb) xb[2 * f - 1] = Ab;
-        }
-        if (f == 0) {  // A_{N/2} = X_{N/2} / N closes the row
-          if (va) xa[N - 1] = v.x * sc;
-          if (vb) xb[N - 1] = v.y * sc;
         }
       }
       // no barrier needed here: the next tile's first write to this exchange tile comes after its landing-read barrier,
