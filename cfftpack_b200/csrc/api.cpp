@@ -587,6 +587,11 @@ const char *cfb200_last_error(void) { return last_error(); }
 void cfb200_release(void) {
   release_plans();
   scratch_release_all();
+  if (t_bounce.p) {
+    cudaFreeHost(t_bounce.p);
+    t_bounce.p = nullptr;
+    t_bounce.tried = false;
+  }
 }
 const char *cfb200_version(void) {
 #ifdef CFB_SIM
