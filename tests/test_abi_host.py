@@ -1,6 +1,6 @@
 """CPU-side checks of the product library's C ABI and host logic (no kernel runs here).
 
- - libcfftpack_b200.so loads and exports every symbol include/cfftpack_b200.h declares;
+ - libcfftpack_b200.so loads and exports every symbol include/cfftpack_b200.h and include/cfftpack_b200_l2.h declare;
  - the *i_ routines fill wsave bit-for-bit like the reference (golden fixture) -- host code;
  - ier codes agree with the oracle for every argument error (all return before any GPU work);
  - without a GPU the library fails loudly (ier = -1) instead of falling back to a CPU path.
@@ -26,12 +26,15 @@ def _declared_symbols():
     for fam in re.findall(r"CFB200_DECL_TRIG\((\w+)\)", src):
         if fam != "name":
             names |= {f"{fam}{v}_" for v in ("1i", "1f", "1b", "mi", "mf", "mb")}
+    # the object API header (cfftpack.h names): every prototype "type name(" at the start of a line
+    l2 = open(os.path.join(fl.ROOT, "include", "cfftpack_b200_l2.h")).read()
+    names |= set(re.findall(r"^(?:int|void|fft_t \*)\s*(\w+)\(", l2, flags=re.M))
     return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
     names = _declared_symbols()
-    assert len(names) >= 9 + 6 + 24 + 8, names
+    assert len(names) >= 9 + 6 + 24 + 8 + 3 + 1 + 24, names
     for n in names:
         assert hasattr(fl.product(), n), n
     # the north_star list, explicitly
