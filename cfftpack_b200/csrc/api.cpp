@@ -309,6 +309,7 @@ static inline long long spanm(int lot, int jump, int n, int inc) {
 /* ---------------- complex ---------------- */
 static int complex_init(int *n, double *wsave, int *lensav, int *ier) {
   *ier = 0;
+  if (*n < 1) return 0;
   if (*lensav < 2 * *n + log2_floor_ref(*n) + 4) {
     *ier = 2;
     return 0;
@@ -320,6 +321,11 @@ static int complex_init(int *n, double *wsave, int *lensav, int *ier) {
 
 static int complex_1d(int *n, int *inc, void *c, int *lenc, int *lensav, int *lenwrk, int *ier, int dir) {
   *ier = 0;
+  if (*n < 1) return 0;  // undefined upstream (log of a non-positive length): nothing to transform
+  if (*inc < 1) {  // undefined upstream; here: the array cannot hold the sequence
+    *ier = 1;
+    return 0;
+  }
   if (*lenc < span1(*n, *inc)) *ier = 1;
   else if (*lensav < 2 * *n + log2_floor_ref(*n) + 4) *ier = 2;
   else if (*lenwrk < 2 * *n) *ier = 3;
@@ -335,6 +341,11 @@ static int complex_1d(int *n, int *inc, void *c, int *lenc, int *lensav, int *le
 static int complex_multi(int *lot, int *jump, int *n, int *inc, void *c, int *lenc, int *lensav, int *lenwrk, int *ier,
                          int dir) {
   *ier = 0;
+  if (*n < 1 || *lot < 1) return 0;  // empty batch: the reference's loops run zero times (lot) / undefined (n)
+  if (*inc < 1 || *jump < 0) {  // undefined upstream; reported as inconsistent strides
+    *ier = 4;
+    return 0;
+  }
   if (*lenc < spanm(*lot, *jump, *n, *inc)) *ier = 1;
   else if (*lensav < 2 * *n + log2_floor_ref(*n) + 4) *ier = 2;
   else if ((long long)*lenwrk < 2LL * *lot * *n) *ier = 3;
@@ -348,6 +359,7 @@ static int complex_multi(int *lot, int *jump, int *n, int *inc, void *c, int *le
 
 static int complex_2d(int *ldim, int *l, int *m, void *c, int *lensav, int *lenwrk, int *ier, int dir) {
   *ier = 0;
+  if (*l < 1 || *m < 1) return 0;
   if (*l > *ldim) *ier = 5;
   else if (*lensav < 2 * *l + log2_floor_ref(*l) + 2 * *m + log2_floor_ref(*m) + 8) *ier = 2;
   else if ((long long)*lenwrk < 2LL * *l * *m) *ier = 3;
@@ -369,6 +381,7 @@ static void real_2d_sizes(int l, int m, int &lw, int &mw, int &mm) {
 static int real_2d(int *ldim, int *l, int *m, double *r, int *lensav, int *lenwrk, int *ier, int dir) {
   int lw, mw, mm;
   *ier = 0;
+  if (*l < 1 || *m < 1) return 0;
   real_2d_sizes(*l, *m, lw, mw, mm);
   if (*lensav < lw + mw + mm) *ier = 2;
   else if ((long long)*lenwrk < ((long long)*l + 1) * *m) *ier = 3;
@@ -401,6 +414,7 @@ static long long fam_lenwrk(int kind, int n, long long lot, bool multi) {
 
 static int real_init(int kind, int *n, double *wsave, int *lensav, int *ier) {
   *ier = 0;
+  if (*n < 1) return 0;
   if (*lensav < fam_lensav(kind, *n)) {
     *ier = 2;
     return 0;
@@ -418,6 +432,11 @@ static int real_init(int kind, int *n, double *wsave, int *lensav, int *ier) {
 
 static int real_1d(int kind, int *n, int *inc, double *x, int *lenx, int *lensav, int *lenwrk, int *ier, int dir) {
   *ier = 0;
+  if (*n < 1) return 0;
+  if (*inc < 1) {
+    *ier = 1;
+    return 0;
+  }
   if (*lenx < span1(*n, *inc)) *ier = 1;
   else if (*lensav < fam_lensav(kind, *n)) *ier = 2;
   else if (*lenwrk < fam_lenwrk(kind, *n, 1, false)) *ier = 3;
@@ -435,6 +454,11 @@ static int real_1d(int kind, int *n, int *inc, double *x, int *lenx, int *lensav
 static int real_multi(int kind, int *lot, int *jump, int *n, int *inc, double *x, int *lenx, int *lensav, int *lenwrk,
                       int *ier, int dir) {
   *ier = 0;
+  if (*n < 1 || *lot < 1) return 0;
+  if (*inc < 1 || *jump < 0) {
+    *ier = 4;
+    return 0;
+  }
   if (*lenx < spanm(*lot, *jump, *n, *inc)) *ier = 1;
   else if (*lensav < fam_lensav(kind, *n)) *ier = 2;
   else if ((long long)*lenwrk < fam_lenwrk(kind, *n, *lot, true)) *ier = 3;

@@ -131,6 +131,33 @@ def test_option_convolution_argument_checks():
         assert (N, ier) == (1024, -1) and not val.any()  # sizes like cfftextra.c:42-46; no CPU path
 
 
+def test_degenerate_arguments_never_touch_data_or_crash():
+    """non-positive n / lot (the reference loops zero times or is undefined) and non-positive strides"""
+    lib = fl.product()
+    x = np.random.default_rng(1).uniform(-1, 1, 256)
+    ws, wk = np.zeros(600), np.zeros(8)
+    for name, (lot, jump, n, inc), want in (("cfftmf_", (-1, 8, 8, 1), 0), ("cfftmf_", (0, 8, 8, 1), 0), ("cfftmb_", (2, 8, 0, 1), 0),
+                                            ("rfftmb_", (0, 8, 8, 1), 0), ("costmf_", (2, 8, -1, 1), 0), ("sinqmb_", (-2, 8, 8, 1), 0),
+                                            ("cfftmf_", (2, 8, 8, -1), 4), ("rfftmf_", (2, -8, 8, 1), 4), ("cosqmf_", (2, 8, 8, 0), 4)):
+        y, ier = x.copy(), I(-7)
+        getattr(lib, name)(ctypes.byref(I(lot)), ctypes.byref(I(jump)), ctypes.byref(I(n)), ctypes.byref(I(inc)), fl.P(y),
+                           ctypes.byref(I(128)), fl.P(ws), ctypes.byref(I(600)), fl.P(wk), ctypes.byref(I(100000)), ctypes.byref(ier))
+        assert ier.value == want and np.array_equal(y, x), (name, lot, jump, n, inc, ier.value)
+    for name, n, inc, want in (("cfft1f_", 0, 1, 0), ("rfft1b_", -4, 1, 0), ("cost1f_", 0, 1, 0), ("cfft1b_", 8, -1, 1), ("sint1f_", 8, 0, 1)):
+        y, ier = x.copy(), I(-7)
+        getattr(lib, name)(ctypes.byref(I(n)), ctypes.byref(I(inc)), fl.P(y), ctypes.byref(I(128)), fl.P(ws), ctypes.byref(I(600)),
+                           fl.P(wk), ctypes.byref(I(1000)), ctypes.byref(ier))
+        assert ier.value == want and np.array_equal(y, x), (name, n, inc, ier.value)
+    ier = I(-7)
+    lib.cfft1i_(ctypes.byref(I(0)), fl.P(ws), ctypes.byref(I(600)), ctypes.byref(ier))
+    assert ier.value == 0 and not ws.any()
+    for fn in ("cfft2f_", "rfft2b_"):
+        y, ier = x.copy(), I(-7)
+        getattr(lib, fn)(ctypes.byref(I(4)), ctypes.byref(I(0)), ctypes.byref(I(4)), fl.P(y), fl.P(ws), ctypes.byref(I(600)),
+                         fl.P(wk), ctypes.byref(I(1000)), ctypes.byref(ier))
+        assert ier.value == 0 and np.array_equal(y, x)
+
+
 def test_length_one_is_a_no_op():
     for fam in fl.FAMILIES:
         x = fl.rand_input(fam, 1, 5)
