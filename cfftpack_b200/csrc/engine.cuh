@@ -560,7 +560,7 @@ __device__ __forceinline__ void real_issue_loads(const EngineParams &P, double *
 }
 
 template <int KIND, int DIR>
-__global__ void __launch_bounds__(CFB_ENGINE_THREADS, 3) engine_kernel(const EngineParams P) {
+__global__ void __launch_bounds__(CFB_ENGINE_REAL_MAXTHREADS, 2) engine_kernel(const EngineParams P) {
   CFB_DYN_SMEM(smem_raw);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int T = P.T, ldz = P.ldz, M = P.M, n = P.n;

@@ -11,6 +11,7 @@ enum Kind { K_C2C = 0, K_RFFT = 1, K_COST = 2, K_SINT = 3, K_COSQ = 4, K_SINQ = 
 
 #define CFB_MAXPASS 24
 #define CFB_ENGINE_THREADS 256
+#define CFB_ENGINE_REAL_MAXTHREADS 384  /* real-family engine kernel: 256, or 384 when a tile holds four rows */
 
 /* generic odd radix: output pairs (k, r-k) one thread computes together from each pair of inputs it loads */
 #define CFB_GENERIC_KB 4
