@@ -120,36 +120,76 @@ bool make_tensor_map3(TensorMap3 *tm, const void *base, unsigned long long d0, u
 #endif
 }
 
-int sm_count() {
-  static int sms = 0;
-  if (!sms) {
+int sm_count() {  // of the calling thread's current device
+  static std::mutex mu;
+  static int sms[64];
+  int d = 0;
+  cudaGetDevice(&d);
+  if (d < 0 || d >= 64) d = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!sms[d]) {
     cudaDeviceProp p;
-    int d = 0;
-    cudaGetDevice(&d);
-    if (cudaGetDeviceProperties(&p, d) == cudaSuccess) sms = p.multiProcessorCount;
-    else sms = 148;
+    sms[d] = cudaGetDeviceProperties(&p, d) == cudaSuccess && p.multiProcessorCount > 0 ? p.multiProcessorCount : 148;
   }
-  return sms;
+  return sms[d];
+}
+
+/* Plan tables: copy on the caller's stream and wait for the DMA itself.  A pageable cudaMemcpy only promises that the
+ * source has been staged, and the non-blocking streams the transforms may run on do not order against the NULL stream. */
+void *upload_table(const void *host, size_t bytes) {
+  void *d = nullptr;
+  if (!cuda_ok(cudaMalloc(&d, bytes ? bytes : 16), "cudaMalloc(plan table)")) return nullptr;
+  if (bytes && !(cuda_ok(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, t_stream), "cudaMemcpyAsync(plan table)") &&
+                 cuda_ok(cudaStreamSynchronize(t_stream), "cudaStreamSynchronize(plan table)"))) {
+    cudaFree(d);
+    return nullptr;
+  }
+  return d;
 }
 
 struct Scratch {
   void *p = nullptr;
   size_t cap = 0;
-  int dev = -1;
 };
+/* Scratch is private to a (host thread, device, stream): transforms issued by one thread on different streams -- the three
+ * streams of the host-array pipeline below, or a caller alternating cfb200_set_stream -- run concurrently on the GPU, so
+ * they must not share intermediates (four-step, chirp-z, long real).  Switching device or stream keeps every set alive. */
 struct ScratchSet {
+  int dev = -1;
+  cudaStream_t stream = 0;
   Scratch s[8];  // 0 four-step, 1 staged host array, 2 chirp-z, 3 long real, 4-6 staging pipeline, 7 rfft2 pairs
-  ~ScratchSet() {
-    for (auto &x : s)
-      if (x.p) cudaFree(x.p);
-  }
 };
-static thread_local ScratchSet t_scr;
+struct ScratchSets {
+  std::vector<ScratchSet *> sets;
+  void free_all() {
+    for (auto *set : sets) {
+      for (auto &x : set->s)
+        if (x.p) cudaFree(x.p);
+      delete set;
+    }
+    sets.clear();
+  }
+  ~ScratchSets() { free_all(); }
+};
+static thread_local ScratchSets t_scr;
 void *scratch_get(int slot, size_t bytes) {
-  Scratch &s = t_scr.s[slot];
   int dev = 0;
   cudaGetDevice(&dev);
-  if (s.cap >= bytes && s.p && s.dev == dev) return s.p;
+  ScratchSet *set = nullptr;
+  for (auto *c : t_scr.sets)
+    if (c->dev == dev && c->stream == t_stream) set = c;
+  if (!set) {
+    if (t_scr.sets.size() >= 16) {  // a caller cycling through short-lived streams: start over rather than grow without bound
+      cudaDeviceSynchronize();
+      t_scr.free_all();
+    }
+    set = new ScratchSet();
+    set->dev = dev;
+    set->stream = t_stream;
+    t_scr.sets.push_back(set);
+  }
+  Scratch &s = set->s[slot];
+  if (s.cap >= bytes && s.p) return s.p;
   if (s.p) {
     cudaStreamSynchronize(t_stream);
     cudaFree(s.p);
@@ -162,16 +202,9 @@ void *scratch_get(int slot, size_t bytes) {
     return nullptr;
   }
   s.cap = cap;
-  s.dev = dev;
   return s.p;
 }
-void scratch_release_all() {
-  for (auto &x : t_scr.s) {
-    if (x.p) cudaFree(x.p);
-    x.p = nullptr;
-    x.cap = 0;
-  }
-}
+void scratch_release_all() { t_scr.free_all(); }
 
 /* Short host arrays (a single cfft1f_ of a few thousand points: config 1) skip the two copy-engine launches: the data
  * is placed in a per-thread pinned, device-mapped bounce buffer that the kernels read and write across PCIe directly. */

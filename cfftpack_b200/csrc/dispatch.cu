@@ -186,8 +186,33 @@ struct PeerOut {
   long long row_inc = 0, row_jump = 0, elem_inc = 0;  // layout on the peers: index = base + m*row_jump + (e % chunk)*elem_inc
 };
 
+static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c,
+                                         double scale, const PeerOut *po);
+
+/* Batches much larger than the L2 cache (126 MB) are walked in lot-chunks whose intermediate (the scratch array
+ * between the two sweeps) stays L2-resident: sweep 1 of a chunk reads HBM and writes L2, sweep 2 reads L2 and writes
+ * HBM, so the whole transform moves each element over the HBM pins once each way instead of twice.
+ * CFB200_FS_CHUNK_MB sets the chunk size (0 = one chunk). */
 static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c,
                                    double scale, const PeerOut *po = nullptr) {
+  static const long long chunk_mb = getenv("CFB200_FS_CHUNK_MB") ? atoll(getenv("CFB200_FS_CHUNK_MB")) : 0;
+  long long per = chunk_mb > 0 ? (chunk_mb << 20) / ((long long)n * (long long)sizeof(cpx)) : lot;
+  per -= per % 256;  // whole tiles of every row length the sweeps use
+  if (per < 256 || per >= lot) return run_c2c_pow2_four_step_chunk(n, a1, a2, lot, inc, jump, dir, c, scale, po);
+  for (long long m0 = 0; m0 < lot; m0 += per) {
+    const long long lc = lot - m0 < per ? lot - m0 : per;
+    PeerOut sub;
+    if (po) {
+      sub = *po;
+      sub.base += m0 * po->row_jump;
+    }
+    if (!run_c2c_pow2_four_step_chunk(n, a1, a2, lc, inc, jump, dir, c + m0 * jump, scale, po ? &sub : nullptr)) return false;
+  }
+  return true;
+}
+
+static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c,
+                                         double scale, const PeerOut *po) {
   const int n1 = 1 << a1, n2 = 1 << a2;
   const RootPlan *rp = get_root_plan(n);
   if (!rp) return false;

@@ -24,6 +24,8 @@ bool kernel_attrs_ready(const void *kernel, size_t smem);
 /* true once a CUDA device is usable; otherwise prints one loud line to stderr (there is no CPU path) */
 bool device_ready();
 int sm_count();
+/* device copy of a host table, complete (not merely staged) on return; nullptr + last_error on failure */
+void *upload_table(const void *host, size_t bytes);
 
 /* grow-only per-thread device scratch (four-step intermediates, staging of host arrays) */
 void *scratch_get(int slot, size_t bytes);

@@ -115,14 +115,7 @@ int cur_dev() {
 
 template <class T>
 T *upload(const std::vector<T> &h) {
-  T *d = nullptr;
-  size_t bytes = (h.size() ? h.size() : 1) * sizeof(T);
-  if (!cuda_ok(cudaMalloc((void **)&d, bytes), "cudaMalloc(plan)")) return nullptr;
-  if (h.size() && !cuda_ok(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy(plan)")) {
-    cudaFree(d);
-    return nullptr;
-  }
-  return d;
+  return (T *)upload_table(h.data(), h.size() * sizeof(T));
 }
 }  // namespace
 
@@ -302,7 +295,14 @@ const ChirpPlan *get_chirp_plan(int n) {
   return pl;
 }
 
+void pow2_release_tables();
+void r10_release_tables();
+
+/* The caller must be quiescent: no other host thread inside a transform (plans are handed out as raw pointers). */
 void release_plans() {
+  cudaDeviceSynchronize();  // kernels in flight may still read the tables
+  pow2_release_tables();
+  r10_release_tables();
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto &kv : g_core) {
     cudaFree(kv.second->d_tw);

@@ -46,12 +46,8 @@ const cpx *pow2_table() {
         }
     }
   }
-  cpx *d = nullptr;
-  if (!cuda_ok(cudaMalloc((void **)&d, h.size() * sizeof(cpx)), "cudaMalloc(pow2 twiddles)")) return nullptr;
-  if (!cuda_ok(cudaMemcpy(d, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy(pow2 twiddles)")) {
-    cudaFree(d);
-    return nullptr;
-  }
+  cpx *d = (cpx *)upload_table(h.data(), h.size() * sizeof(cpx));
+  if (!d) return nullptr;
   g_tw[key] = d;
   return d;
 }
@@ -80,12 +76,8 @@ const cpx *pow2_stream_table() {
         ++o;
       }
   }
-  cpx *d = nullptr;
-  if (!cuda_ok(cudaMalloc((void **)&d, h.size() * sizeof(cpx)), "cudaMalloc(pow2 twiddles)")) return nullptr;
-  if (!cuda_ok(cudaMemcpy(d, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy(pow2 twiddles)")) {
-    cudaFree(d);
-    return nullptr;
-  }
+  cpx *d = (cpx *)upload_table(h.data(), h.size() * sizeof(cpx));
+  if (!d) return nullptr;
   g_tw[key] = d;
   return d;
 }
@@ -93,18 +85,6 @@ const cpx *pow2_stream_table() {
 template <class K>
 bool set_smem_once(K kernel, size_t smem) {
   return kernel_attrs_ready((const void *)kernel, smem);
-}
-
-template <class C, int MINB, int DIR>
-bool launch_c2c_cfg(long long lot, long long jump, cpx *c, double scale) {
-  const cpx *tw = pow2_table<C>();
-  if (!tw) return false;
-  auto kern = pow2_c2c_kernel<C, MINB, DIR>;
-  if (!set_smem_once(kern, C::SMEM)) return false;
-  const long long grid = (lot + C::TPB - 1) / C::TPB;
-  CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, C::SMEM, current_stream(), c, lot, jump, tw, scale);
-  count_launch();
-  return cuda_ok(cudaGetLastError(), "pow2_c2c_kernel launch");
 }
 
 template <class C, int MINB, int DIR>
@@ -149,67 +129,6 @@ bool launch_r2c_stream(long long lot, long long jump, double *r) {
   return cuda_ok(cudaGetLastError(), "pow2_r2c_stream_kernel launch");
 }
 
-/* half-length real kernel: stage tables of the length-M transform followed by w_N^t, t = 0..NT */
-template <class C>
-const cpx *pow2_half_table() {
-  typedef StreamSmem<C> S;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> lk(g_mu);
-  int l2 = 0;
-  while ((1 << l2) < C::N) ++l2;
-  auto key = std::make_tuple(dev, l2, C::LP, 200);
-  auto it = g_tw.find(key);
-  if (it != g_tw.end()) return it->second;
-  std::vector<cpx> h((size_t)S::TWS_COUNT + HalfSmem<C>::WT);
-  size_t o = 0;
-  for (int st = 0; st < C::NFULL; ++st) {
-    if (C::stage_last(st)) continue;
-    const int m = C::stage_m(st);
-    const long long ncur = (long long)m * C::P;
-    for (int e = 1; e <= 4; e += 3)
-      for (int p = 0; p < m; ++p) {
-        unit_root((long long)p * e, ncur, &h[o].x, &h[o].y);
-        ++o;
-      }
-  }
-  for (int t = 0; t <= C::NT; ++t, ++o) unit_root(t, 2LL * C::N, &h[o].x, &h[o].y);
-  cpx *d = nullptr;
-  if (!cuda_ok(cudaMalloc((void **)&d, h.size() * sizeof(cpx)), "cudaMalloc(pow2 twiddles)")) return nullptr;
-  if (!cuda_ok(cudaMemcpy(d, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy(pow2 twiddles)")) {
-    cudaFree(d);
-    return nullptr;
-  }
-  g_tw[key] = d;
-  return d;
-}
-
-template <int LOG2N, int THREADS, int DIR>
-bool launch_r2c_half(long long lot, long long jump, double *r) {
-  typedef Pow2Cfg<LOG2N - 1, 4, 1, THREADS> C;
-  constexpr int MINB = (HalfSmem<C>::BYTES > 110 * 1024) ? 1 : (HalfSmem<C>::BYTES > 56 * 1024 ? 2 : (THREADS <= 128 ? 4 : 2));
-  const cpx *tw = pow2_half_table<C>();
-  if (!tw) return false;
-  auto kern = pow2_r2c_half_kernel<C, MINB, DIR>;
-  if (!set_smem_once(kern, HalfSmem<C>::BYTES)) return false;
-  const long long ntiles = (lot + C::TPB - 1) / C::TPB;
-  const long long cap = (long long)MINB * sm_count();
-  const long long grid = ntiles < cap ? ntiles : cap;
-  CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, HalfSmem<C>::BYTES, current_stream(), r, lot, jump, tw, ntiles);
-  count_launch();
-  return cuda_ok(cudaGetLastError(), "pow2_r2c_half_kernel launch");
-}
-
-/* tuning knob for experiments (N = 4096 only): CFB200_POW2_VARIANT, see DESIGN.md */
-int variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("CFB200_POW2_VARIANT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
 template <int LOG2N>
 struct StreamMinB {
   static constexpr int value = LOG2N >= 13 ? 1 : (Pow2Cfg<LOG2N>::LP == 3 ? 4 : 2);
@@ -217,31 +136,13 @@ struct StreamMinB {
 
 template <int LOG2N, int DIR>
 bool launch_c2c(long long lot, long long jump, cpx *c, double scale) {
-  if (LOG2N == 12) {
-    switch (variant()) {
-      case 1: return launch_c2c_cfg<Pow2Cfg<12, 4, 0>, 2, DIR>(lot, jump, c, scale);  // direct loads, table twiddles, 2 CTAs/SM
-      case 2: return launch_c2c_cfg<Pow2Cfg<12, 4, 1>, 2, DIR>(lot, jump, c, scale);  // direct loads, rebuilt twiddles
-      case 3: return launch_c2c_cfg<Pow2Cfg<12, 4, 1>, 3, DIR>(lot, jump, c, scale);  // ... 3 CTAs/SM (spills)
-      case 4: return launch_c2c_cfg<Pow2Cfg<12, 3, 1>, 2, DIR>(lot, jump, c, scale);  // 8 points/thread, 512 threads
-      case 6: return launch_c2c_stream<Pow2Cfg<12, 3, 1>, 2, DIR>(lot, jump, c, scale);  // streaming, 8 points/thread
-      default: break;
-    }
-  }
   return launch_c2c_stream<Pow2Cfg<LOG2N>, StreamMinB<LOG2N>::value, DIR>(lot, jump, c, scale);
 }
 template <int LOG2N, int DIR>
 bool launch_r2c(long long lot, long long jump, double *r) {
   // the bulk-copy engine needs 16-byte aligned rows: odd jumps (or an odd base) take the direct-load kernel
   const bool tma_ok = (jump % 2 == 0) && (((uintptr_t)r & 15) == 0);
-  if (!tma_ok || (LOG2N == 12 && variant() == 1))
-    return launch_r2c_cfg<Pow2Cfg<LOG2N>, (LOG2N >= 13 ? 1 : 2), DIR>(lot, jump, r);
-  if (LOG2N == 12) {
-    // experiment: CFB200_R2C_HALF=1|2 selects the half-length single-row kernel with 256 / 128 threads per
-    // CTA.  Measured 1.00 / 0.86 ms against 0.82 ms for the pair kernel at N = 4096, lot = 65536, so it is off by default.
-    static const int half = getenv("CFB200_R2C_HALF") ? atoi(getenv("CFB200_R2C_HALF")) : 0;
-    if (half == 1) return launch_r2c_half<12, 256, DIR>(lot, jump, r);
-    if (half == 2) return launch_r2c_half<12, 128, DIR>(lot, jump, r);
-  }
+  if (!tma_ok) return launch_r2c_cfg<Pow2Cfg<LOG2N>, (LOG2N >= 13 ? 1 : 2), DIR>(lot, jump, r);
   return launch_r2c_stream<Pow2Cfg<LOG2N>, StreamMinB<LOG2N>::value, DIR>(lot, jump, r);
 }
 
@@ -306,25 +207,14 @@ bool launch_tile(TileParams &P) {
     const bool layout_ok = !P.in_staged && P.ain.jump_lo == 1 && P.ain.nlo % C::TPB == 0 && P.lot % P.ain.nlo == 0 &&
                            (((uintptr_t)P.in) & 15) == 0 && P.ain.inc > 0 && P.ain.jump_hi >= 0 &&
                            (unsigned long long)P.ain.inc * 16 < (1ULL << 40) && (unsigned long long)P.ain.jump_hi * 16 < (1ULL << 40);
-    static const int small_cta = getenv("CFB200_TILE_THREADS") ? atoi(getenv("CFB200_TILE_THREADS")) == 128 : 0;
-    typedef Pow2Cfg<LOG2N, 4, 1, 128> C1;
-    const bool layout1_ok = layout_ok && P.ain.nlo % C1::TPB == 0;
-    if (!no_tma && small_cta && LOG2N <= 8 && box_ok && layout1_ok) {
-      ok = launch_tile_tma<(LOG2N <= 8 ? LOG2N : 8), DIR, false, 128>(P, &declined);
-      if (!declined) return ok;
-    }
     if (!no_tma && box_ok && layout_ok && TileTmaSmem<C, false>::bytes(P.fs_count) <= SMEM_LIMIT) {
       ok = launch_tile_tma<LOG2N, DIR, false>(P, &declined);
       if (!declined) return ok;
     }
     const bool rows_ok = P.in_staged && P.ain.inc == 1 && (((uintptr_t)P.in) & 15) == 0;
-    if (!no_tma && small_cta && LOG2N <= 8 && rows_ok) return launch_tile_tma<(LOG2N <= 8 ? LOG2N : 8), DIR, true, 128>(P, &declined);
     if (!no_tma && rows_ok && TileTmaSmem<C, true>::bytes(P.fs_count) <= SMEM_LIMIT) return launch_tile_tma<LOG2N, DIR, true>(P, &declined);
   }
   static const bool direct = getenv("CFB200_TILE_DIRECT") != nullptr;
-  static const bool wide = getenv("CFB200_TILE_WIDE") != nullptr;  // experiment: 512-thread CTAs, twice the rows per tile
-  if (wide && LOG2N <= 7 && TileStreamSmem<Pow2Cfg<LOG2N, 4, 1, 512>>::bytes(P.fs_count) <= SMEM_LIMIT)
-    return launch_tile_stream<(LOG2N <= 7 ? LOG2N : 7), DIR, 512>(P);
   if (!direct && TileStreamSmem<Pow2Cfg<LOG2N, 4, 1>>::bytes(P.fs_count) <= SMEM_LIMIT) return launch_tile_stream<LOG2N, DIR>(P);
   typedef Pow2Cfg<LOG2N, 4, 0> C;
   P.tw = pow2_table<C>();
@@ -376,6 +266,12 @@ bool pow2_r2c_supported(int n, long long inc, long long jump, int) {
     case 13: return dir < 0 ? FN<13, -1>(__VA_ARGS__) : FN<13, 1>(__VA_ARGS__); \
     default: break;                                                   \
   }
+
+void pow2_release_tables() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto &kv : g_tw) cudaFree(kv.second);
+  g_tw.clear();
+}
 
 int pow2_tile_min_log2() { return 6; }
 int pow2_tile_max_log2() { return 10; }

@@ -138,25 +138,6 @@ __device__ __forceinline__ void pow2_core(cpx (&a)[C::P], cpx *__restrict__ sm, 
   }
 }
 
-template <class C, int MINB, int DIR>
-__global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_kernel(cpx *__restrict__ c, long long lot, long long jump,
-                                                                    const cpx *__restrict__ tw, double scale) {
-  CFB_DYN_SMEM(smem_raw);
-  const int tl = threadIdx.x / C::NT, t = threadIdx.x % C::NT;
-  const long long g = (long long)blockIdx.x * C::TPB + tl;
-  const bool live = g < lot;
-  cpx *sm = (cpx *)smem_raw + (size_t)tl * C::TILE;
-  cpx *x = c + (live ? g : 0) * jump + t;
-  cpx a[C::P];
-#pragma unroll
-  for (int i = 0; i < C::P; ++i) a[i] = live ? x[C::NT * i] : make_double2(0.0, 0.0);
-  pow2_core<C, DIR>(a, sm, t, tw);
-  if (live) {
-#pragma unroll
-    for (int i = 0; i < C::P; ++i) x[C::NT * i] = make_double2(a[i].x * scale, a[i].y * scale);
-  }
-}
-
 /* two real sequences per complex transform.  DIR = -1: rfftmf_ (x -> scaled half-complex, fftpack.c:10281-10349),
  * DIR = +1: rfftmb_ (half-complex -> x). */
 template <class C, int MINB, int DIR>
@@ -475,147 +456,6 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
       for (int i = 0; i < P; ++i) {
         if (va) xa[t + NT * i] = a[i].x;
         if (vb) xb[t + NT * i] = a[i].y;
-      }
-    }
-  }
-}
-
-/* ---------------------------------------------------------------------------------------------------------
- * Real sequences, one at a time, as a HALF-LENGTH complex transform: the row x[0..N) read as z[j] = x[2j] + i x[2j+1]
- * (j < M = N/2) is already the packed complex sequence, so the landing buffer is consumed with 16-byte loads and every
- * row is independent (no pairing, no odd-lot tail).  Forward: Z = FFT_M(z), then with E/O the transforms of the even/odd
- * samples, E2 = Z[k] + conj Z[M-k], O2 = -i (Z[k] - conj Z[M-k]), T2 = w_N^k O2:
- *     2 X[k] = E2 + T2,   2 X[M-k] = conj(E2 - T2),   X[0], X[M] = Re Z[0] +- Im Z[0],   X[M/2] = conj Z[M/2].
- * Thread t holds k = t + NT i; the partners Z[M-k] of its lower 8 slots are the upper 8 slots of thread NT-t, passed
- * through the exchange tile once.  w_N^k = w_N^t * w_32^i: one shared-memory table entry and a compile-time constant.
- * Backward: the inverse relations rebuild Z from the half-complex row, then one inverse FFT_M leaves x in place order.
- * Output/input format: FFTPACK's [X0, A1, B1, ..., A_M] with A_f = 2 Re X_f / N, B_f = -2 Im X_f / N (rfftf1_ epilogue,
- * fftpack.c:13818-13853); 16-byte aligned pairs are (B_f, A_f+1), completed by a lane shuffle as in the pair kernel.
- * --------------------------------------------------------------------------------------------------------- */
-template <class C>
-struct HalfSmem {
-  typedef StreamSmem<C> S;
-  static constexpr int WT = C::NT + 1;  // w_N^t, t = 0..NT
-  static constexpr size_t BYTES = S::LAND + S::XCH + S::TWS + (size_t)WT * sizeof(cpx) + 16;
-};
-/* e^{-2 pi i j / 32}, j = 0..8 (j is a compile-time constant after unrolling) */
-__device__ __forceinline__ cpx root32(int j) {
-  switch (j) {
-    case 0: return make_double2(1.0, 0.0);
-    case 1: return make_double2(0.98078528040323044913, -0.19509032201612826785);
-    case 2: return make_double2(0.92387953251128675613, -0.38268343236508977173);
-    case 3: return make_double2(0.83146961230254523708, -0.55557023301960222474);
-    case 4: return make_double2(0.70710678118654752440, -0.70710678118654752440);
-    case 5: return make_double2(0.55557023301960222474, -0.83146961230254523708);
-    case 6: return make_double2(0.38268343236508977173, -0.92387953251128675613);
-    case 7: return make_double2(0.19509032201612826785, -0.98078528040323044913);
-    default: return make_double2(0.0, -1.0);
-  }
-}
-
-template <class C, int MINB, int DIR>
-__global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_half_kernel(double *__restrict__ r, long long lot,
-                                                                         long long jump, const cpx *__restrict__ tw,
-                                                                         long long ntiles) {
-  CFB_DYN_SMEM(smem_raw);
-  constexpr int M = C::N, N = 2 * M, P = C::P, NT = C::NT;
-  static_assert(P == 16 && NT % 32 == 0, "half-length real kernel: 16 points per thread, whole warps per row");
-  typedef StreamSmem<C> S;
-  cpx *land = (cpx *)smem_raw;  // [TPB][M] complex = [TPB][N] real
-  double *xch = (double *)(smem_raw + S::LAND);
-  cpx *tws = (cpx *)(smem_raw + S::LAND + S::XCH);
-  cpx *wts = (cpx *)(smem_raw + S::LAND + S::XCH + S::TWS);
-  uint64_t *bar = (uint64_t *)(wts + HalfSmem<C>::WT);
-  const int tid = threadIdx.x, tl = tid / NT, t = tid % NT, lane = tid & 31;
-  if (tid == 0) mbar_init(bar, 1);
-  for (int i = tid; i < S::TWS_COUNT; i += C::THREADS) tws[i] = __ldg(tw + i);
-  for (int i = tid; i < HalfSmem<C>::WT; i += C::THREADS) wts[i] = __ldg(tw + S::TWS_COUNT + i);
-  __syncthreads();
-  long long tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) stream_issue<C::TPB>((char *)land, (const char *)r, lot, jump * 8, tile, N * 8, bar);
-  unsigned parity = 0;
-  double *xq = xch + (size_t)tl * S::XTILE;
-  const cpx w_t = wts[t], w_r = wts[NT - t];
-  for (; tile < ntiles; tile += gridDim.x) {
-    mbar_wait(bar, parity);
-    parity ^= 1;
-    const long long g = tile * C::TPB + tl;
-    const bool live = g < lot;
-    double *xo = r + (live ? g : 0) * jump;
-    cpx a[P];
-    if (DIR < 0) {
-#pragma unroll
-      for (int i = 0; i < P; ++i) a[i] = land[(size_t)tl * M + t + NT * i];
-    } else {
-      const double *lr = (const double *)(land + (size_t)tl * M);
-#pragma unroll
-      for (int i = 0; i < P; ++i) {
-        const int e = t + NT * i;
-        if (e == 0) a[i] = make_double2(lr[0] + lr[N - 1], lr[0] - lr[N - 1]);
-        else if (e == M / 2) a[i] = make_double2(lr[M - 1], lr[M]);
-        else {
-          const bool low = i < P / 2;
-          const int k = low ? e : M - e;
-          // Y[k] = (A_k, -B_k)/2 and conj Y[M-k] = (A_{M-k}, B_{M-k})/2 (rfftb1_ convention)
-          const double px = 0.5 * lr[2 * k - 1], py = -0.5 * lr[2 * k], qx = 0.5 * lr[2 * (M - k) - 1], qy = 0.5 * lr[2 * (M - k)];
-          const cpx wk = low ? cmul(w_t, root32(i)) : cmul(w_r, root32(P - 1 - i));
-          const cpx W = cmulc(make_double2(px - qx, py - qy), wk);  // conj(w^k) (Y[k] - conj Y[M-k])
-          const double sx = px + qx, sy = py + qy;
-          a[i] = low ? make_double2(sx - W.y, sy + W.x) : make_double2(sx + W.y, W.x - sy);
-        }
-      }
-    }
-    __syncthreads();  // the landing buffer has been consumed: refill it with the next tile while we compute
-    const long long next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
-    pow2_core_split<C, DIR>(a, xq, t, tws);
-    if (DIR < 0) {
-      cpx *zq = (cpx *)xq;  // M/2 complex slots: Z[M/2 + j] at slot j
-#pragma unroll
-      for (int i = P / 2; i < P; ++i) zq[t + NT * (i - P / 2)] = a[i];
-      __syncthreads();
-      const double sc = 1.0 / (double)N;
-#pragma unroll
-      for (int i = 0; i < P / 2; ++i) {
-        const int k = t + NT * i;
-        const cpx u = a[i], v = zq[k == 0 ? 0 : M / 2 - k];
-        double Ak, Bk, Am, Bm;
-        if (k == 0) {  // Z[0] -> X[0], X[M];  slot 0 holds Z[M/2] -> X[M/2] = conj Z[M/2]
-          Ak = 0.0;
-          Bk = (u.x + u.y) * sc;
-          Am = (u.x - u.y) * sc;
-          Bm = 0.0;
-          if (live) {
-            xo[M - 1] = 2.0 * v.x * sc;
-            xo[M] = 2.0 * v.y * sc;
-          }
-        } else {
-          const double ex = u.x + v.x, ey = u.y - v.y;
-          const cpx T = cmul(cmul(w_t, root32(i)), make_double2(u.y + v.y, v.x - u.x));
-          Ak = (ex + T.x) * sc;
-          Bk = -(ey + T.y) * sc;
-          Am = (ex - T.x) * sc;
-          Bm = (ey - T.y) * sc;
-        }
-        const double Ak_n = __shfl_down_sync(0xffffffffu, Ak, 1), Am_p = __shfl_up_sync(0xffffffffu, Am, 1);
-        if (live) {
-          // ascending half: pair (B_k, A_{k+1}) at 2k
-          if (lane < 31 && t != NT - 1) *(double2 *)(xo + 2 * k) = make_double2(Bk, Ak_n);
-          else xo[2 * k] = Bk;
-          if (lane == 0 && k != 0) xo[2 * k - 1] = Ak;
-          // descending half f = M - k: pair (B_f, A_{f+1}) at 2f, A_{f+1} held by the previous lane
-          const int f = M - k;
-          if (lane > 0) *(double2 *)(xo + 2 * f) = make_double2(Bm, Am_p);
-          else if (k != 0) xo[2 * f] = Bm;
-          if (lane == 31) xo[2 * f - 1] = Am;
-        }
-      }
-      // no barrier needed: the next write to this exchange tile comes after the next landing-read barrier
-    } else {
-      if (live) {
-        cpx *y = (cpx *)xo + t;
-#pragma unroll
-        for (int i = 0; i < P; ++i) y[NT * i] = a[i];
       }
     }
   }
@@ -967,6 +807,7 @@ bool pow2_r2c_launch(int n, long long lot, long long jump, int dir, double *r);
 int pow2_tile_min_log2();
 int pow2_tile_max_log2();
 bool pow2_tile_launch(int log2n, int dir, TileParams &P);
+void pow2_release_tables();
 
 }  // namespace cfb
 #endif

@@ -34,12 +34,8 @@ const cpx *r10_table() {
         ++o;
       }
   }
-  cpx *d = nullptr;
-  if (!cuda_ok(cudaMalloc((void **)&d, h.size() * sizeof(cpx)), "cudaMalloc(radix-10 twiddles)")) return nullptr;
-  if (!cuda_ok(cudaMemcpy(d, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy(radix-10 twiddles)")) {
-    cudaFree(d);
-    return nullptr;
-  }
+  cpx *d = (cpx *)upload_table(h.data(), h.size() * sizeof(cpx));
+  if (!d) return nullptr;
   g_tw[key] = d;
   return d;
 }
@@ -88,6 +84,12 @@ bool launch_r2c(long long lot, long long jump, double *r, const double *trig) {
   return cuda_ok(cudaGetLastError(), "r10_r2c_stream_kernel launch");
 }
 }  // namespace
+
+void r10_release_tables() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto &kv : g_tw) cudaFree(kv.second);
+  g_tw.clear();
+}
 
 bool r10_cost_launch(long long npairs, int dir, double *x, const double *trig) {
   typedef R10Cfg<3> C;

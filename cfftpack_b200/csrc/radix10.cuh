@@ -565,6 +565,7 @@ bool r10_r2c_launch(int n, long long lot, long long jump, int dir, double *r);
 bool r10_cosq_launch(int n, long long lot, long long jump, int dir, double *x, const double *trig);
 /* costmf_/costmb_ n = 1001, contiguous rows, an even number of rows */
 bool r10_cost_launch(long long npairs, int dir, double *x, const double *trig);
+void r10_release_tables();
 
 }  // namespace cfb
 #endif

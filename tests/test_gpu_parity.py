@@ -242,6 +242,33 @@ def test_known_answers():
     assert np.max(np.abs(r - want)) < 1e-14
 
 
+def _sample_rows(lot, count):
+    """>= `count` sequences: the first and last tiles plus an odd-stride walk over the whole lot"""
+    if lot <= count:
+        return np.arange(lot)
+    rng = np.random.default_rng(lot)
+    walk = (np.arange(count) * ((lot // count) | 1) + 3) % lot
+    return np.unique(np.concatenate([np.arange(8), np.arange(lot - 8, lot), walk, rng.integers(0, lot, 64)]))
+
+
+def _sampled_rows_vs_oracle(torch, fam, d, n, lot, x_in, x_out, count=1024, jump=None, inc=1):
+    """>= count sampled sequences of a device-resident batch against the CPU oracle, each to the north_star bar.
+    Arrays are float64 tensors (complex as interleaved pairs); layout (jump, inc) in elements, default contiguous."""
+    jump = n if jump is None else jump
+    rows = _sample_rows(lot, count)
+    esz = 2 if fam == "cfft" else 1
+    idx = torch.as_tensor(rows[:, None] * jump + inc * np.arange(n)[None, :], device=x_in.device)  # [rows][n] elements
+    xi = x_in.view(-1, esz)[idx.reshape(-1)].cpu().numpy().reshape(-1)
+    xo = x_out.view(-1, esz)[idx.reshape(-1)].cpu().numpy().reshape(-1)
+    if fam == "cfft":
+        xi, xo = xi.view(np.complex128), xo.view(np.complex128)
+    want, ier = ORC.runm(fam, d, len(rows), n, n, 1, xi)
+    assert ier == 0
+    err = np.array([fl.rel_l2(xo[j * n:(j + 1) * n], want[j * n:(j + 1) * n]) for j in range(len(rows))])
+    assert err.max() <= fl.tol(n), (fam, d, n, lot, int(rows[err.argmax()]), float(err.max()))
+    return float(err.max())
+
+
 def _torch():
     import torch
     return torch
@@ -260,12 +287,7 @@ def test_device_pointers_full_size_config2_properties():
     before = cb.launch_count()
     assert plan.multi("f", x.data_ptr(), lot, n, 1, lot * n) == 0
     cb.synchronize()
-    sample = [0, 1, 777, 32768, 65535]
-    want_in = np.stack([torch.view_as_complex(x0[i * n:(i + 1) * n]).cpu().numpy() for i in sample]).ravel()
-    want, ier = ORC.runm("cfft", "f", len(sample), n, n, 1, want_in)
-    got = np.stack([torch.view_as_complex(x[i * n:(i + 1) * n]).cpu().numpy() for i in sample]).ravel()
-    for j in range(len(sample)):
-        assert fl.rel_l2(got[j * n:(j + 1) * n], want[j * n:(j + 1) * n]) <= fl.tol(n)
+    _sampled_rows_vs_oracle(torch, "cfft", "f", n, lot, x0, x)
     assert plan.multi("b", x.data_ptr(), lot, n, 1, lot * n) == 0
     cb.synchronize()
     assert cb.launch_count() >= before + 2
@@ -289,14 +311,11 @@ def test_device_pointers_full_size_config3_properties():
     plan = cb.Plan("rfft", n)
     assert plan.multi("f", x.data_ptr(), lot, n, 1, lot * n) == 0
     cb.synchronize()
-    sample = [0, 1, 4097, 65534, 65535]
-    want_in = np.concatenate([x0[i * n:(i + 1) * n].cpu().numpy() for i in sample])
-    want, ier = ORC.runm("rfft", "f", len(sample), n, n, 1, want_in)
-    got = np.concatenate([x[i * n:(i + 1) * n].cpu().numpy() for i in sample])
-    for j in range(len(sample)):
-        assert fl.rel_l2(got[j * n:(j + 1) * n], want[j * n:(j + 1) * n]) <= fl.tol(n)
+    _sampled_rows_vs_oracle(torch, "rfft", "f", n, lot, x0, x)
+    xf = x.clone()
     assert plan.multi("b", x.data_ptr(), lot, n, 1, lot * n) == 0
     cb.synchronize()
+    _sampled_rows_vs_oracle(torch, "rfft", "b", n, lot, xf, x)
     err = (x - x0).norm() / x0.norm()
     assert float(err) <= fl.tol(n), float(err)
 
@@ -312,13 +331,11 @@ def test_device_pointers_config4_roundtrip_and_sample():
         plan = cb.Plan(fam, n)
         assert plan.multi("f", x.data_ptr(), lot, n, 1, lot * n) == 0, cb.last_error()
         cb.synchronize()
-        sample = [0, 1, 12345, 32767]
-        want_in = np.concatenate([x0[i * n:(i + 1) * n].cpu().numpy() for i in sample])
-        want, ier = ORC.runm(fam, "f", len(sample), n, n, 1, want_in)
-        got = np.concatenate([x[i * n:(i + 1) * n].cpu().numpy() for i in sample])
-        for j in range(len(sample)):
-            assert fl.rel_l2(got[j * n:(j + 1) * n], want[j * n:(j + 1) * n]) <= fl.tol(n), (fam, n)
+        _sampled_rows_vs_oracle(torch, fam, "f", n, lot, x0, x)
+        xf = x.clone()
         assert plan.multi("b", x.data_ptr(), lot, n, 1, lot * n) == 0
+        cb.synchronize()
+        _sampled_rows_vs_oracle(torch, fam, "b", n, lot, xf, x, count=256)
         cb.synchronize()
         err = float((x - x0).norm() / x0.norm())
         assert err <= fl.tol(n), (fam, n, err)
@@ -356,6 +373,88 @@ def test_cfft2_16384_device_roundtrip_and_separability():
     back = (v[:, None] * u[None, :])
     err = float((torch.view_as_real(c) - torch.view_as_real(back)).norm() / torch.view_as_real(back).norm())
     assert err <= fl.tol(l * m), err
+
+
+def test_interleaved_layout_full_size_config2():
+    """BASELINE config 2 in the reference's own "vector" layout (jump=1, inc=lot; test/ftest.c:64):
+    N=4096, lot=65536, >= 1024 sampled sequences against the oracle, forward and back."""
+    torch = _torch()
+    import cfftpack_b200 as cb
+    n, lot = 4096, 65536
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = torch.rand(lot * n, 2, generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    x0 = x.clone()
+    plan = cb.Plan("cfft", n)
+    assert plan.multi("f", x.data_ptr(), lot, 1, lot, lot * n) == 0, cb.last_error()
+    cb.synchronize()
+    _sampled_rows_vs_oracle(torch, "cfft", "f", n, lot, x0, x, jump=1, inc=lot)
+    assert plan.multi("b", x.data_ptr(), lot, 1, lot, lot * n) == 0
+    cb.synchronize()
+    err = float((x - x0).norm() / x0.norm())
+    assert err <= fl.tol(n), err
+
+
+def test_cfft2_16384_nonseparable_sampled_rows_and_columns():
+    """BASELINE config 5 at full size on a NON-separable random matrix: 36 full output columns and 35 full output rows
+    against the oracle's 1-D transforms of the single-bin DFT sums along the other dimension (bench.cfft2_parity),
+    then forward+backward is the identity.  Catches any misplaced element of the four-step transposes."""
+    torch = _torch()
+    import cfftpack_b200 as cb
+    import bench
+    l = m = 16384
+    x_in = bench.slab_input(torch, l, m, 0)
+    c = x_in.clone()
+    lib = fl.product()
+    ws, ls, ier = PROD.init2(l, m)
+    I = ctypes.c_int
+    ierc, dummy = I(-1), ctypes.c_double(0)
+    args = (ctypes.byref(I(l)), ctypes.byref(I(l)), ctypes.byref(I(m)), ctypes.c_void_p(c.data_ptr()), fl.P(ws),
+            ctypes.byref(I(ls)), ctypes.byref(dummy), ctypes.byref(I(2**31 - 1)), ctypes.byref(ierc))
+    lib.cfft2f_(*args)
+    cb.synchronize()
+    assert ierc.value == 0, lib.cfb200_last_error()
+    err, ncols, nrows = bench.cfft2_parity(torch, None, x_in, c, l, m, 0, 1)
+    assert ncols >= 32 and nrows >= 32
+    assert err <= fl.tol(l * m), err
+    lib.cfft2b_(*args)
+    cb.synchronize()
+    back = float((torch.view_as_real(c) - torch.view_as_real(x_in)).norm() / torch.view_as_real(x_in).norm())
+    assert back <= fl.tol(l * m), back
+
+
+def test_pipelined_staging_with_scratch_using_lengths():
+    """the host-array pipeline runs lot-chunks concurrently on three streams; lengths whose transform
+    needs device scratch (four-step 16384, chirp-z prime, long real) must not share it between chunks.  The chunk size
+    is lowered through CFB200_PIPE_CHUNK_KB (read once per process, hence the subprocess) so that small batches take
+    the pipelined path with many chunks in flight; results must equal the device-pointer path bit for bit."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import cfftpack_b200 as cb
+bad = 0
+for fam, n, lot in (("cfft", 16384, 96), ("cfft", 10007, 64), ("rfft", 32768, 96), ("cost", 10001, 64), ("cfft", 4096, 512)):
+    esz = 2 if fam == "cfft" else 1
+    h = torch.empty(lot * n * esz, dtype=torch.float64, pin_memory=True).uniform_(-1, 1)
+    d = h.cuda()
+    plan = cb.Plan(fam, n)
+    for rep in range(3):
+        hh = h.clone().pin_memory()
+        dd = d.clone()
+        assert plan.multi("f", dd.data_ptr(), lot, n, 1, lot * n) == 0, cb.last_error()
+        cb.synchronize()
+        assert plan.multi("f", hh.data_ptr(), lot, n, 1, lot * n) == 0, cb.last_error()
+        if not torch.equal(hh, dd.cpu()):
+            bad += 1
+            print("MISMATCH", fam, n, lot, rep, float((hh - dd.cpu()).abs().max()))
+print("BAD", bad)
+sys.exit(1 if bad else 0)
+""" % fl.ROOT
+    env = dict(os.environ, CFB200_PIPE_CHUNK_KB="1024")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-2000:])
 
 
 def test_pinned_host_arrays_take_the_pipelined_path():
