@@ -426,7 +426,7 @@ def test_pipelined_staging_with_scratch_using_lengths():
     """the host-array pipeline runs lot-chunks concurrently on three streams; lengths whose transform
     needs device scratch (four-step 16384, chirp-z prime, long real) must not share it between chunks.  The chunk size
     is lowered through CFB200_PIPE_CHUNK_KB (read once per process, hence the subprocess) so that small batches take
-    the pipelined path with many chunks in flight; results must equal the device-pointer path bit for bit."""
+    the pipelined path with many chunks in flight; results must equal the device-pointer path (bit for bit for complex data)."""
     import os
     import subprocess
     import sys
@@ -446,9 +446,13 @@ for fam, n, lot in (("cfft", 16384, 96), ("cfft", 10007, 64), ("rfft", 32768, 96
         assert plan.multi("f", dd.data_ptr(), lot, n, 1, lot * n) == 0, cb.last_error()
         cb.synchronize()
         assert plan.multi("f", hh.data_ptr(), lot, n, 1, lot * n) == 0, cb.last_error()
-        if not torch.equal(hh, dd.cpu()):
+        # complex: bit for bit.  Real families pair rows (z = x_a + i x_b) inside a chunk, so a chunk boundary at an odd
+        # row re-pairs them and moves the rounding by an ulp; a scratch race would be a gross error.
+        ref_ = dd.cpu()
+        same = torch.equal(hh, ref_) if fam == "cfft" else float((hh - ref_).norm() / ref_.norm()) <= 1e-14
+        if not same:
             bad += 1
-            print("MISMATCH", fam, n, lot, rep, float((hh - dd.cpu()).abs().max()))
+            print("MISMATCH", fam, n, lot, rep, float((hh - ref_).abs().max()))
 print("BAD", bad)
 sys.exit(1 if bad else 0)
 """ % fl.ROOT
