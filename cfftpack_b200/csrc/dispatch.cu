@@ -17,6 +17,7 @@
 #include "plan.h"
 #include "pow2.cuh"
 #include "radix10.cuh"
+#include "mixed3.cuh"
 
 namespace cfb {
 
@@ -634,6 +635,20 @@ bool run_real(int kind, int n, long long lot, long long inc, long long jump, int
     const TrigPlan *tp = get_trig_plan(K_COST, n);
     if (!tp) return false;
     if (!r10_cost_launch(lot / 2, dir, x, tp->d_trig)) return false;
+    if (lot % 2 == 0) return true;
+    x += (lot - 1) * jump;
+    lot = 1;
+  }
+  static const bool no_m3 = getenv("CFB200_NO_M3") != nullptr;  // A/B switch: the general engine instead
+  if (!no_m3 && m3_supported(kind, n) && inc == 1 && jump == n && lot >= 2 && (((uintptr_t)x) & 15) == 0) {
+    // 13*11*7 register kernel on the pairs of rows; a last odd row goes through the general engine
+    const double *trig = nullptr;
+    if (kind != K_RFFT) {
+      const TrigPlan *tp = get_trig_plan(kind, n);
+      if (!tp) return false;
+      trig = tp->d_trig;
+    }
+    if (!m3_launch(kind, n, lot / 2, dir, x, trig)) return false;
     if (lot % 2 == 0) return true;
     x += (lot - 1) * jump;
     lot = 1;

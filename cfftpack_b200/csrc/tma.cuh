@@ -48,6 +48,18 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
 __device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
   bulk_g2s(smem_dst, gsrc, bytes, bar);
 }
+/* shared -> global bulk store (emulated: an immediate copy, so the group waits are no-ops) */
+__device__ __forceinline__ void fence_async_smem() {}
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, unsigned bytes) {
+  if ((((uintptr_t)smem_src) | ((uintptr_t)gdst) | bytes) & 15) {
+    fprintf(stderr, "cfbsim: cp.async.bulk (store) needs 16-byte aligned addresses and size (%p <- %p, %u)\n", gdst, smem_src, bytes);
+    abort();
+  }
+  memcpy(gdst, smem_src, bytes);
+}
+__device__ __forceinline__ void bulk_commit() {}
+__device__ __forceinline__ void bulk_wait_read() {}
+__device__ __forceinline__ void bulk_wait_all() {}
 /* box load: dense [box1][box0] doubles at smem_dst, zero fill outside the tensor */
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const TensorMap3 *tm, uint64_t *bar, int c0, int c1, int c2) {
   double *d = (double *)smem_dst;
@@ -132,6 +144,18 @@ __device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
+/* ---- shared -> global bulk stores (SASS UBLKCP.G.S): one instruction drains a finished row from shared memory ----
+ * every thread that wrote the source executes fence_async_smem() before the barrier that precedes the store */
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+/* the issuing thread: all of its committed stores have finished READING shared memory (the source may be reused) */
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+/* ... have completed entirely (writes visible) */
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 #endif
 
 }  // namespace cfb
