@@ -538,6 +538,36 @@ def run_cfft2(args, torch, dist, cb, rank, local_rank, world, barrier):
             flush=True)
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank's host threads on the CPUs of the NUMA node its GPU hangs off, so that the pinned staging buffers
+    of the end-to-end leg are first-touched (and therefore placed) next to the GPU's PCIe root instead of all ranks
+    sharing node 0.  Best effort: returns a description, never raises."""
+    try:
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bdf is None:
+            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bdf = out
+        bdf = bdf.lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]  # sysfs uses a 4-digit PCI domain
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"numa_node": node, "bound": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as ex:
+        return {"numa_node": None, "bound": False, "why": str(ex)[:80]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -575,6 +605,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: cfftpack_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -660,11 +692,15 @@ def main():
         nbytes = lot * n * esz * 8
         e2e = {"value": world * bytes_rank / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-               "note": f"host pinned array -> {fam}mf_ C ABI -> host; copies inside the timed region"}
+               "note": f"host pinned array -> {fam}mf_ C ABI -> host; copies inside the timed region", "host_numa": numa}
         del h
     except Exception as ex:  # report, never hide
         e2e = {"value": None, "unit": "GB/s", "error": str(ex)}
 
+    try:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every host core again
+    except Exception:
+        pass
     peak, peak_src = hbm_peak()
     kern_ms = sorted(per_launch_ms)[len(per_launch_ms) // 2]
     avg_ms = sum(per_launch_ms) / len(per_launch_ms)
