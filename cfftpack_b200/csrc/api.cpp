@@ -157,7 +157,7 @@ struct Scratch {
 struct ScratchSet {
   int dev = -1;
   cudaStream_t stream = 0;
-  Scratch s[8];  // 0 four-step, 1 staged host array, 2 chirp-z, 3 long real, 4-6 staging pipeline, 7 rfft2 pairs
+  Scratch s[10];  // 0 four-step, 1 staged host array, 2 chirp-z, 3 long real, 4-6 staging pipeline, 7 rfft2 pairs, 8 long 1-D
 };
 struct ScratchSets {
   std::vector<ScratchSet *> sets;
@@ -628,6 +628,17 @@ int cfb200_cfft2_sharded_phase(int phase, int direction, int l, int m, int rank,
   }
   if (!device_ready() || !run_c2c_2d_sharded_phase(phase, direction < 0 ? -1 : +1, l, m, rank, nranks, local_src, peer_dst))
     *ier = -1;
+  return 0;
+}
+
+int cfb200_cfft1_sharded_phase(int phase, int direction, int log2n, int rank, int nranks, void *local_src,
+                               void *const *peer_dst, int *ier) {
+  *ier = 0;
+  if (phase < 0 || phase > 2 || nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks || !local_src || !peer_dst) {
+    *ier = 1;
+    return 0;
+  }
+  if (!device_ready() || !run_c2c_1d_sharded_phase(phase, direction < 0 ? -1 : +1, log2n, rank, nranks, local_src, peer_dst)) *ier = -1;
   return 0;
 }
 

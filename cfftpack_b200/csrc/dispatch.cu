@@ -187,19 +187,34 @@ struct PeerOut {
   long long row_inc = 0, row_jump = 0, elem_inc = 0;  // layout on the peers: index = base + m*row_jump + (e % chunk)*elem_inc
 };
 
-static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c,
-                                         double scale, const PeerOut *po);
+/* optional second twiddle of the long 1-D decomposition (TileParams::tw2): results of sequence i, output index b, times W_N^(i b) */
+struct Tw2 {
+  const RootPlan *rp = nullptr;  // roots of N
+  long long n = 0, off = 0;      // N, index of the first sequence
+};
+/* out-of-place form: sequences (inc, jump) of `cin` -> (inc_out, jump_out) of `cout` */
+struct FourStepIO {
+  const cpx *cin;
+  long long inc, jump;
+  cpx *cout;
+  long long inc_out, jump_out;
+};
+static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, const FourStepIO &io, int dir, double scale,
+                                         const PeerOut *po, const Tw2 *tw2);
 
 /* Batches much larger than the L2 cache (126 MB) are walked in lot-chunks whose intermediate (the scratch array
  * between the two sweeps) stays L2-resident: sweep 1 of a chunk reads HBM and writes L2, sweep 2 reads L2 and writes
  * HBM, so the whole transform moves each element over the HBM pins once each way instead of twice.
  * CFB200_FS_CHUNK_MB sets the chunk size (0 = one chunk). */
 static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c,
-                                   double scale, const PeerOut *po = nullptr) {
+                                   double scale, const PeerOut *po = nullptr, const Tw2 *tw2 = nullptr) {
   static const long long chunk_mb = getenv("CFB200_FS_CHUNK_MB") ? atoll(getenv("CFB200_FS_CHUNK_MB")) : 0;
   long long per = chunk_mb > 0 ? (chunk_mb << 20) / ((long long)n * (long long)sizeof(cpx)) : lot;
   per -= per % 256;  // whole tiles of every row length the sweeps use
-  if (per < 256 || per >= lot) return run_c2c_pow2_four_step_chunk(n, a1, a2, lot, inc, jump, dir, c, scale, po);
+  if (per < 256 || per >= lot) {
+    const FourStepIO io = {c, inc, jump, c, inc, jump};
+    return run_c2c_pow2_four_step_chunk(n, a1, a2, lot, io, dir, scale, po, tw2);
+  }
   for (long long m0 = 0; m0 < lot; m0 += per) {
     const long long lc = lot - m0 < per ? lot - m0 : per;
     PeerOut sub;
@@ -207,13 +222,31 @@ static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long lo
       sub = *po;
       sub.base += m0 * po->row_jump;
     }
-    if (!run_c2c_pow2_four_step_chunk(n, a1, a2, lc, inc, jump, dir, c + m0 * jump, scale, po ? &sub : nullptr)) return false;
+    Tw2 t2;
+    if (tw2) {
+      t2 = *tw2;
+      t2.off += m0;
+    }
+    const FourStepIO io = {c + m0 * jump, inc, jump, c + m0 * jump, inc, jump};
+    if (!run_c2c_pow2_four_step_chunk(n, a1, a2, lc, io, dir, scale, po ? &sub : nullptr, tw2 ? &t2 : nullptr)) return false;
   }
   return true;
 }
 
-static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c,
-                                         double scale, const PeerOut *po) {
+static void set_tw2(TileParams &P, const Tw2 *tw2, int seq_lo, int n1) {
+  if (!tw2 || !tw2->rp) return;
+  P.tw2 = tw2->rp->d_w;
+  P.tw2_shift = tw2->rp->shift;
+  P.tw2_mask = tw2->n - 1;
+  P.tw2_off = tw2->off;
+  P.tw2_seq_lo = seq_lo;
+  P.tw2_n1 = n1;
+}
+
+static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, const FourStepIO &io, int dir, double scale,
+                                         const PeerOut *po, const Tw2 *tw2) {
+  const long long inc = io.inc, jump = io.jump;
+  const cpx *c = io.cin;
   const int n1 = 1 << a1, n2 = 1 << a2;
   const RootPlan *rp = get_root_plan(n);
   if (!rp) return false;
@@ -244,20 +277,23 @@ static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, l
   P.in_staged = 0;
   if (!pow2_tile_launch(a1, dir, P)) return false;
   // step 2: rows (m, k1), transform over j2 (length n2), output element k2 goes to index k1 + n1*k2
+  const long long oinc = io.inc_out, ojump = io.jump_out;
   P.in = scr;
-  P.out = c;
+  P.out = io.cout;
   P.lot = lot * n1;
   P.scale = scale;
   P.fs = nullptr;
   P.fs_count = 0;
   if (!batch_fast) {  // row g = m*n1 + k1: scratch rows are contiguous along j2 -> staged load
     P.ain = make_addr(1, n2, n, n1);
-    P.aout = make_addr((long long)n1 * inc, inc, jump, n1);
+    P.aout = make_addr((long long)n1 * oinc, oinc, ojump, n1);
     P.in_staged = 1;
+    set_tw2(P, tw2, 0, n1);
   } else {  // row g = k1*lot + m
     P.ain = make_addr(lot, 1, (long long)n2 * lot, lot);
-    P.aout = make_addr((long long)n1 * inc, jump, inc, lot);
+    P.aout = make_addr((long long)n1 * oinc, ojump, oinc, lot);
     P.in_staged = 0;
+    set_tw2(P, tw2, 1, n1);
   }
   if (po && po->npeers > 0) {
     // output element k = k1 + n1*e of sequence m lives on peer k / chunk at base + m*row_jump + (k % chunk)*elem_inc
@@ -275,6 +311,69 @@ static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, l
     else P.aout = make_addr((long long)n1 * po->elem_inc, po->row_jump, po->elem_inc, lot);
   }
   return pow2_tile_launch(a2, dir, P);
+}
+
+/* one sweep of the tile kernel: `lot` sequences of length 2^a (a in 6..10), any in/out layout, optional second twiddle */
+static bool run_c2c_pow2_single_sweep(int a, long long lot, const FourStepIO &io, int dir, double scale, const Tw2 *tw2) {
+  if (lot > 2147483647LL) {
+    set_error("batch too large");
+    return false;
+  }
+  TileParams P;
+  memset(&P, 0, sizeof(P));
+  P.in = io.cin;
+  P.out = io.cout;
+  P.lot = lot;
+  P.scale = scale;
+  P.ain = make_addr(io.inc, io.jump, 0, lot);
+  P.aout = make_addr(io.inc_out, io.jump_out, 0, lot);
+  P.in_staged = io.inc == 1 ? 1 : 0;
+  set_tw2(P, tw2, 1, 1);  // rows are (hi = 0, lo = sequence): output index b = element
+  return pow2_tile_launch(a, dir, P);
+}
+
+/* `lot` sequences of length n = 2^a, a in {6..10} (one sweep) or {12..20} (four-step), out of place */
+static bool run_c2c_pow2_sub(int a, long long lot, const FourStepIO &io, int dir, double scale, const Tw2 *tw2) {
+  if (a <= pow2_tile_max_log2()) return run_c2c_pow2_single_sweep(a, lot, io, dir, scale, tw2);
+  const int a1 = a / 2, a2 = a - a1;
+  return run_c2c_pow2_four_step_chunk(1 << a, a1, a2, lot, io, dir, scale, nullptr, tw2);
+}
+
+/* split of a long power-of-two length 2^a into 2^aL * 2^aM with both parts served by run_c2c_pow2_sub */
+static bool long_pow2_split(int a, int *aL, int *aM) {
+  if (a < 21 || a > 30) return false;
+  *aL = a >= 24 ? a / 2 : (a == 21 ? 9 : 10);
+  *aM = a - *aL;
+  return true;
+}
+
+/* Power-of-two lengths beyond the four-step range (2^21 .. 2^30): N = L * Mm, x[i + L j] (i < L, j < Mm)
+ *   A. for every i: transform over j (length Mm, stride L), results times W_N^(i b)   -> T[i + L b]
+ *   B. for every b: transform over i (length L, contiguous)                            -> X[Mm a + b]
+ * Each part is itself a four-step pair of sweeps (or one sweep when short), so a 2^28-point transform is four sweeps.
+ * The reference does any N in core with log(N) sweeps (c1fm1f_, cfftpack/fftpack.c:2041-2141). */
+static bool run_c2c_long_pow2(int a, long long lot, long long inc, long long jump, int dir, cpx *c, double scale) {
+  int aL, aM;
+  if (!long_pow2_split(a, &aL, &aM)) {
+    set_error("power-of-two length 2^%d is outside the supported range (<= 2^30)", a);
+    return false;
+  }
+  const long long N = 1LL << a, L = 1LL << aL, Mm = 1LL << aM;
+  const RootPlan *rp = get_root_plan((int)N);
+  if (!rp) return false;
+  cpx *T = (cpx *)scratch_get(8, (size_t)N * sizeof(cpx));
+  if (!T) return false;
+  Tw2 tw2;
+  tw2.rp = rp;
+  tw2.n = N;
+  for (long long m = 0; m < lot; ++m) {
+    cpx *x = c + m * jump;
+    const FourStepIO ioA = {x, L * inc, inc, T, L, 1};  // sequences i (jump = inc), elements j (stride L inc) -> T[i + L b]
+    if (!run_c2c_pow2_sub(aM, L, ioA, dir, 1.0, &tw2)) return false;
+    const FourStepIO ioB = {T, 1, L, x, Mm * inc, inc};  // sequences b (jump L), elements i -> x[(Mm a + b) inc]
+    if (!run_c2c_pow2_sub(aL, Mm, ioB, dir, scale, nullptr)) return false;
+  }
+  return true;
 }
 
 /* lengths with a prime factor beyond the four-step split: chirp-z through power-of-two transforms */
@@ -355,6 +454,7 @@ bool run_c2c_scaled(int n, long long lot, long long inc, long long jump, int dir
     while ((1 << a) < n) ++a;
     const int a1 = a / 2, a2 = a - a1;
     if (a1 >= pow2_tile_min_log2() && a2 <= pow2_tile_max_log2()) return run_c2c_pow2_four_step(n, a1, a2, lot, inc, jump, dir, (cpx *)c, scale);
+    if (a > 2 * pow2_tile_max_log2()) return run_c2c_long_pow2(a, lot, inc, jump, dir, (cpx *)c, scale);
   }
   const int n1 = four_step_split(n, engine_max_c2c());
   if (n1 <= 1) return run_c2c_bluestein(n, lot, inc, jump, dir, (cpx *)c, scale);  // a prime factor too large to split
@@ -450,6 +550,74 @@ bool run_c2c_2d_sharded_phase(int phase, int dir, int l, int m, int rank, int nr
   po.row_jump = 1;    // sequence i_loc -> row rank*l_loc + i_loc of C
   po.elem_inc = l;    // output index j_loc -> column j_loc of C (pitch l)
   return run_c2c_pow2_four_step(m, a1, a2, l_loc, l_loc, 1, dir, (cpx *)src, dir < 0 ? 1.0 / (double)m : 1.0, &po);
+}
+
+/* ---- very long 1-D transforms across GPUs: N = L * Mm, the array distributed in natural order
+ * (rank r owns x[r N/G .. (r+1) N/G) = the columns j of x[i + L j] in its slab).  Three phases, each followed by a
+ * barrier among the ranks (the caller's job, as for the 2-D transform):
+ *   phase 0: transpose only -- my column slab C[m_loc][L] goes to the row slabs D_r[j][i_loc] of the GPUs owning i;
+ *   phase 1: on my row slab D: length-Mm transforms over j, results times W_N^(i b), stored into the column slabs
+ *            C_r[(b % m_loc) L + i] of the GPUs owning b (the exchange rides on the last pass, as in the 2-D case);
+ *   phase 2: on my column slab C: length-L transforms over i, result X[Mm a + b] stored into natural order on the GPU
+ *            owning a: D_r[(a % l_loc) Mm + b].
+ * The result therefore ends in the D buffers, in natural order.  Forward scales by 1/N in total. */
+struct TransposeParams {
+  const cpx *src;
+  cpx *peers[16];
+  long long L, l_loc, m_loc, base;  // base = rank * m_loc * l_loc
+  int shift;                        // log2(l_loc)
+};
+__global__ void __launch_bounds__(256) p2p_transpose_kernel(const TransposeParams P) {
+  const long long total = P.m_loc * P.L, stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const long long j = idx / P.L, i = idx - j * P.L;
+    P.peers[i >> P.shift][P.base + j * P.l_loc + (i & (P.l_loc - 1))] = P.src[idx];
+  }
+}
+
+bool run_c2c_1d_sharded_phase(int phase, int dir, int log2n, int rank, int nranks, void *src, void *const *peers) {
+  const int aL = log2n / 2, aM = log2n - aL;
+  if (log2n < 24 || log2n > 30 || nranks < 1 || nranks > 16 || (nranks & (nranks - 1)) || aM > 2 * pow2_tile_max_log2()) {
+    set_error("sharded 1-D transform: needs N = 2^24 .. 2^30 and a power-of-two number of ranks <= 16");
+    return false;
+  }
+  const long long N = 1LL << log2n, L = 1LL << aL, Mm = 1LL << aM, l_loc = L / nranks, m_loc = Mm / nranks;
+  if (phase == 0) {
+    TransposeParams P;
+    memset(&P, 0, sizeof(P));
+    P.src = (const cpx *)src;
+    for (int i = 0; i < nranks; ++i) P.peers[i] = (cpx *)peers[i];
+    P.L = L;
+    P.l_loc = l_loc;
+    P.m_loc = m_loc;
+    P.base = (long long)rank * m_loc * l_loc;
+    while ((1LL << P.shift) < l_loc) ++P.shift;
+    CFB_LAUNCH(p2p_transpose_kernel, (unsigned)(8 * sm_count()), 256, 0, current_stream(), P);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "p2p_transpose_kernel launch");
+  }
+  PeerOut po;
+  po.npeers = nranks;
+  po.peers = (cpx *const *)peers;
+  if (phase == 1) {
+    const RootPlan *rp = get_root_plan((int)N);
+    if (!rp) return false;
+    Tw2 tw2;
+    tw2.rp = rp;
+    tw2.n = N;
+    tw2.off = (long long)rank * l_loc;
+    po.chunk = m_loc;
+    po.base = (long long)rank * l_loc;
+    po.row_jump = 1;
+    po.elem_inc = L;
+    return run_c2c_pow2_four_step((int)Mm, aM / 2, aM - aM / 2, l_loc, l_loc, 1, dir, (cpx *)src, dir < 0 ? 1.0 / (double)Mm : 1.0, &po,
+                                  &tw2);
+  }
+  po.chunk = l_loc;
+  po.base = (long long)rank * m_loc;
+  po.row_jump = 1;
+  po.elem_inc = Mm;
+  return run_c2c_pow2_four_step((int)L, aL / 2, aL - aL / 2, m_loc, 1, L, dir, (cpx *)src, dir < 0 ? 1.0 / (double)L : 1.0, &po);
 }
 
 bool run_c2c_2d(int ldim, int l, int m, int dir, void *c) {

@@ -50,6 +50,7 @@ bool run_real(int kind, int n, long long lot, long long inc, long long jump, int
 bool run_c2c_2d(int ldim, int l, int m, int dir, void *c);
 bool run_real_2d(int ldim, int l, int m, int dir, double *r);
 bool run_c2c_2d_sharded_phase(int phase, int dir, int l, int m, int rank, int nranks, void *src, void *const *peers);
+bool run_c2c_1d_sharded_phase(int phase, int dir, int log2n, int rank, int nranks, void *src, void *const *peers);
 
 /* batched option valuation (option.cu): par = host [8][lot] (S K sigma theta kappa t r flags), value = host [lot] */
 int next_fast_even_size(int n);

@@ -487,7 +487,68 @@ struct TileParams {
   cpx *peers[16];
   int npeers, peer_shift;
   long long out_base;
+  // long 1-D transforms N = L*Mm (six-step): the results of the length-Mm transforms (this sweep computes elements
+  // b = tw2_k0(row) + tw2_n1 * e of sequence i) are multiplied by W_N^(i b) on store.  tw2 = RootPlan table of N in global
+  // memory (2^tw2_shift low entries, then the high ones); the sequence index i is the row's lo (tw2_seq_lo) or hi part
+  // plus tw2_off (first sequence of this GPU / chunk).  nullptr: none.
+  const cpx *tw2;
+  int tw2_shift, tw2_seq_lo, tw2_n1;
+  long long tw2_mask, tw2_off;
 };
+
+/* the last step of every tile kernel: scale, optional twiddles, store to `out` or straight into the peers' slabs */
+template <class C, int DIR>
+__device__ __forceinline__ void tile_store(const TileParams &P, cpx (&a)[C::P], const long long g, const int t,
+                                           const cpx *__restrict__ fss) {
+  constexpr int PP = C::P, NT = C::NT;
+  const long long hi = g / P.aout.nlo, lo = g - hi * P.aout.nlo;
+  const long long oout = hi * P.aout.jump_hi + lo * P.aout.jump_lo;
+  const double scale = P.scale;
+#pragma unroll
+  for (int i = 0; i < PP; ++i) a[i] = make_double2(a[i].x * scale, a[i].y * scale);
+  if (P.fs_count > 0) {
+    // four-step twiddles W_n^(j (t + NT i)) = base * step^i: base, step and step^4 from the split tables in shared
+    // memory (six reads instead of two per element), the powers as in twiddle_powers
+    const int j = (int)(P.fs_from_hi ? hi : lo);
+    const int mask = (1 << P.fs_shift) - 1, sh = P.fs_shift, nmask = P.fs_nmask;
+    auto root = [&](int x) { return cmul(fss[x & mask], fss[mask + 1 + (x >> sh)]); };
+    const cpx b0 = root(j * t), w1 = root((j * NT) & nmask), w4 = root((4 * j * NT) & nmask);
+    cpx b[PP];
+#pragma unroll
+    for (int i = 0; i < PP; ++i) b[i] = b0;
+    twiddle_powers<-1>(b, w1, w4);  // b[i] = b0 * w1^i
+#pragma unroll
+    for (int i = 0; i < PP; ++i) a[i] = ctw<DIR>(a[i], b[i]);
+  }
+  if (P.tw2) {
+    const long long seq = (P.tw2_seq_lo ? lo : hi) + P.tw2_off, k0 = P.tw2_seq_lo ? hi : lo;
+    const long long mask = P.tw2_mask, step = (seq * P.tw2_n1) & mask;
+    const long long lmask = (1LL << P.tw2_shift) - 1;
+    const int sh = P.tw2_shift;
+    auto root = [&](long long x) { return cmul(__ldg(P.tw2 + (x & lmask)), __ldg(P.tw2 + lmask + 1 + (x >> sh))); };
+    const cpx b0 = root((seq * k0 + step * t) & mask), w1 = root((step * NT) & mask), w4 = root((4 * step * NT) & mask);
+    cpx b[PP];
+#pragma unroll
+    for (int i = 0; i < PP; ++i) b[i] = b0;
+    twiddle_powers<-1>(b, w1, w4);
+#pragma unroll
+    for (int i = 0; i < PP; ++i) a[i] = ctw<DIR>(a[i], b[i]);
+  }
+  if (P.npeers > 0) {
+    // fused transpose: each element is stored straight into the memory of the GPU that owns its slab
+    const int emask = (1 << P.peer_shift) - 1;
+#pragma unroll
+    for (int i = 0; i < PP; ++i) {
+      const int e = t + NT * i;
+      P.peers[e >> P.peer_shift][P.out_base + oout + (long long)(e & emask) * P.aout.inc] = a[i];
+    }
+  } else {
+    cpx *y = P.out + oout + (long long)t * P.aout.inc;
+    const long long st = (long long)NT * P.aout.inc;
+#pragma unroll
+    for (int i = 0; i < PP; ++i) y[i * st] = a[i];
+  }
+}
 
 template <class C>
 struct TileSmem {
@@ -511,7 +572,7 @@ __global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_kernel(const TilePara
   const int tid = threadIdx.x, tl = tid % TPB, t = tid / TPB;
   const long long g = (long long)blockIdx.x * TPB + tl;
   const bool live = g < P.lot;
-  const long long oin = live ? tile_batch_off(P.ain, g) : 0, oout = live ? tile_batch_off(P.aout, g) : 0;
+  const long long oin = live ? tile_batch_off(P.ain, g) : 0;
   for (int i = tid; i < P.fs_count; i += C::THREADS) fss[i] = __ldg(P.fs + i);
   cpx *sm = tile + (size_t)tl * PITCH;
   cpx a[PP];
@@ -550,34 +611,7 @@ __global__ void __launch_bounds__(C::THREADS, 2) pow2_tile_kernel(const TilePara
     __syncthreads();
   }
   pow2_core<C, DIR>(a, sm, t, P.tw);
-  if (live && P.npeers > 0) {
-    // fused transpose: each element is stored straight into the memory of the GPU that owns its slab
-    const double scale = P.scale;
-    const int emask = (1 << P.peer_shift) - 1;
-#pragma unroll
-    for (int i = 0; i < PP; ++i) {
-      const int e = t + NT * i;
-      cpx *dst = P.peers[e >> P.peer_shift] + P.out_base + oout + (long long)(e & emask) * P.aout.inc;
-      *dst = make_double2(a[i].x * scale, a[i].y * scale);
-    }
-  } else if (live) {
-    cpx *y = P.out + oout + (long long)t * P.aout.inc;
-    const long long st = (long long)NT * P.aout.inc;
-    const double scale = P.scale;
-    if (P.fs_count > 0) {
-      const int j = (int)(P.fs_from_hi ? g / P.aout.nlo : g % P.aout.nlo);
-      const int mask = (1 << P.fs_shift) - 1, sh = P.fs_shift;
-#pragma unroll
-      for (int i = 0; i < PP; ++i) {
-        const int x = j * (t + NT * i);  // < long length
-        const cpx w = cmul(fss[x & mask], fss[mask + 1 + (x >> sh)]);
-        y[i * st] = ctw<DIR>(make_double2(a[i].x * scale, a[i].y * scale), w);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < PP; ++i) y[i * st] = make_double2(a[i].x * scale, a[i].y * scale);
-    }
-  }
+  if (live) tile_store<C, DIR>(P, a, g, t, fss);
 }
 
 /* Streaming form of the tile kernel: persistent CTAs; the rows of tile k+1 are gathered with per-thread cp.async
@@ -662,39 +696,7 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS > 256 ? 1 : 2)) pow2_t
     if (next < ntiles) tile_issue_loads<C>(P, land, rowoff + ((it + 1) & 1) * TPB, next, tid);
     else cp_async_commit();
     pow2_core_split<C, DIR, false>(a, xr, t, tws);
-    if (live) {
-      const long long oout = tile_batch_off(P.aout, g);
-      const double scale = P.scale;
-      if (P.npeers > 0) {
-        const int emask = (1 << P.peer_shift) - 1;
-#pragma unroll
-        for (int i = 0; i < PP; ++i) {
-          const int e = t + NT * i;
-          cpx *dst = P.peers[e >> P.peer_shift] + P.out_base + oout + (long long)(e & emask) * P.aout.inc;
-          *dst = make_double2(a[i].x * scale, a[i].y * scale);
-        }
-      } else {
-        cpx *y = P.out + oout + (long long)t * P.aout.inc;
-        const long long st = (long long)NT * P.aout.inc;
-        if (P.fs_count > 0) {
-          // four-step twiddles W_n^(j (t + NT i)) = base * step^i: base, step and step^4 from the split tables
-          // (six shared-memory reads instead of two per element), the powers as in twiddle_powers
-          const int j = (int)(P.fs_from_hi ? g / P.aout.nlo : g % P.aout.nlo);
-          const int mask = (1 << P.fs_shift) - 1, sh = P.fs_shift, nmask = P.fs_nmask;
-          auto root = [&](int x) { return cmul(fss[x & mask], fss[mask + 1 + (x >> sh)]); };
-          const cpx base = root(j * t), w1 = root((j * NT) & nmask), w4 = root((4 * j * NT) & nmask);
-          cpx b[PP];
-#pragma unroll
-          for (int i = 0; i < PP; ++i) b[i] = base;
-          twiddle_powers<-1>(b, w1, w4);  // b[i] = base * w1^i (i >= 1)
-#pragma unroll
-          for (int i = 0; i < PP; ++i) y[i * st] = ctw<DIR>(make_double2(a[i].x * scale, a[i].y * scale), b[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < PP; ++i) y[i * st] = make_double2(a[i].x * scale, a[i].y * scale);
-        }
-      }
-    }
+    if (live) tile_store<C, DIR>(P, a, g, t, fss);
   }
   cp_async_wait<0>();
 }
@@ -764,37 +766,7 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS <= 128 ? 4 : 2)) pow2_
     const long long next = tile + gridDim.x;
     if (tid < 32 && next < ntiles) issue(next);
     pow2_core_split<C, DIR, false>(a, xr, t, tws);
-    if (live) {
-      const long long oout = tile_batch_off(P.aout, g);
-      const double scale = P.scale;
-      if (P.npeers > 0) {
-        const int emask = (1 << P.peer_shift) - 1;
-#pragma unroll
-        for (int i = 0; i < PP; ++i) {
-          const int e = t + NT * i;
-          cpx *dst = P.peers[e >> P.peer_shift] + P.out_base + oout + (long long)(e & emask) * P.aout.inc;
-          *dst = make_double2(a[i].x * scale, a[i].y * scale);
-        }
-      } else {
-        cpx *y = P.out + oout + (long long)t * P.aout.inc;
-        const long long st = (long long)NT * P.aout.inc;
-        if (P.fs_count > 0) {
-          const int j = (int)(P.fs_from_hi ? g / P.aout.nlo : g % P.aout.nlo);
-          const int mask = (1 << P.fs_shift) - 1, sh = P.fs_shift, nmask = P.fs_nmask;
-          auto root = [&](int x) { return cmul(fss[x & mask], fss[mask + 1 + (x >> sh)]); };
-          const cpx b0 = root(j * t), w1 = root((j * NT) & nmask), w4 = root((4 * j * NT) & nmask);
-          cpx b[PP];
-#pragma unroll
-          for (int i = 0; i < PP; ++i) b[i] = b0;
-          twiddle_powers<-1>(b, w1, w4);
-#pragma unroll
-          for (int i = 0; i < PP; ++i) y[i * st] = ctw<DIR>(make_double2(a[i].x * scale, a[i].y * scale), b[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < PP; ++i) y[i * st] = make_double2(a[i].x * scale, a[i].y * scale);
-        }
-      }
-    }
+    if (live) tile_store<C, DIR>(P, a, g, t, fss);
   }
 }
 

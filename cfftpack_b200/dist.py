@@ -149,3 +149,64 @@ class Cfft2ShardedP2P:
 
     def backward(self):
         return self.transform("b")
+
+
+class Cfft1ShardedP2P:
+    """Very long 1-D complex transform (cfft1f_/cfft1b_ semantics, cfftpack/fftpack.c:2199, :2151) of N = 2^log2n points
+    distributed in natural order over the ranks of one node: four-step N = L * Mm with the three
+    exchanges fused into the kernels as P2P stores (`cfb200_cfft1_sharded_phase`), one stream-ordered barrier per phase.
+
+    `x` is this rank's chunk x[rank N/G : (rank+1) N/G] (complex128, symmetric memory): fill it, call forward() or
+    backward(); the result -- natural order, this rank's chunk of X -- is returned as a view of the second buffer."""
+
+    def __init__(self, log2n, group=None, lib=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        if lib is None:
+            from . import lib as product_lib
+            lib = product_lib
+        self.lib = lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.log2n, self.n = log2n, 1 << log2n
+        if self.n % self.world:
+            raise ValueError("N must be a multiple of the number of ranks")
+        self.n_loc = self.n // self.world
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._x = symm_mem.empty(self.n_loc * 2, dtype=torch.float64, device=dev)
+        self._y = symm_mem.empty(self.n_loc * 2, dtype=torch.float64, device=dev)
+        self._hx = symm_mem.rendezvous(self._x, self.group)
+        self._hy = symm_mem.rendezvous(self._y, self.group)
+        self.x = torch.view_as_complex(self._x.view(self.n_loc, 2))
+        self.y = torch.view_as_complex(self._y.view(self.n_loc, 2))
+        G = self.world
+        self._x_ptrs = (ctypes.c_void_p * G)(*[int(p) for p in self._hx.buffer_ptrs])
+        self._y_ptrs = (ctypes.c_void_p * G)(*[int(p) for p in self._hy.buffer_ptrs])
+
+    def _phase(self, phase, direction, src, peers):
+        ier = _I(-1)
+        self.lib.cfb200_cfft1_sharded_phase(_I(phase), _I(-1 if direction == "f" else 1), _I(self.log2n), _I(self.rank),
+                                            _I(self.world), ctypes.c_void_p(src), peers, ctypes.byref(ier))
+        if ier.value:
+            from . import last_error
+            raise RuntimeError(f"cfb200_cfft1_sharded_phase({phase}): ier={ier.value}: {last_error()}")
+
+    def transform(self, direction):
+        import torch
+        self.lib.cfb200_set_stream(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._hy.barrier(channel=0)   # every rank is done with Y from the previous call
+        self._phase(0, direction, self._x.data_ptr(), self._y_ptrs)
+        self._hy.barrier(channel=0)   # all row slabs are complete
+        self._phase(1, direction, self._y.data_ptr(), self._x_ptrs)
+        self._hx.barrier(channel=0)   # all column slabs are complete (and every Y has been consumed)
+        self._phase(2, direction, self._x.data_ptr(), self._y_ptrs)
+        self._hy.barrier(channel=0)   # the natural-order result is complete
+        return self.y
+
+    def forward(self):
+        return self.transform("f")
+
+    def backward(self):
+        return self.transform("b")

@@ -99,6 +99,17 @@ int cfb200_option_convolution(int lot, int n, const double *S, const double *K, 
  * divisible by nranks.  ier: 0 ok, 1 bad argument, -1 CUDA failure / unsupported size (cfb200_last_error()). */
 int cfb200_cfft2_sharded_phase(int phase, int direction, int l, int m, int rank, int nranks, void *local_src,
                                void *const *peer_dst, int *ier);
+/* Very long 1-D complex transform (cfft1f_/cfft1b_ semantics, cfftpack/fftpack.c:2199, :2151) of N = 2^log2n points
+ * (24 <= log2n <= 30) distributed in natural order over `nranks` GPUs of one node: rank r holds x[r N/G .. (r+1) N/G).
+ * Four-step decomposition N = L * Mm (L = 2^(log2n/2)) with the exchanges fused into the transform kernels as P2P stores
+ * (SURVEY 8(e) row 3).  Two symmetric buffers of N/nranks complex elements per rank, X (the data) and Y:
+ *   phase 0: local_src = my X, peer_dst = every rank's Y   (transpose only)
+ *   phase 1: local_src = my Y, peer_dst = every rank's X   (length-Mm transforms, twiddles W_N^(i b))
+ *   phase 2: local_src = my X, peer_dst = every rank's Y   (length-L transforms, natural-order scatter)
+ * with a barrier among the ranks after each phase (caller).  The result is in Y, natural order, scaled by 1/N when
+ * direction < 0.  ier as for cfb200_cfft2_sharded_phase. */
+int cfb200_cfft1_sharded_phase(int phase, int direction, int log2n, int rank, int nranks, void *local_src,
+                               void *const *peer_dst, int *ier);
 /* CUDA stream (cudaStream_t) used by THIS host thread for device-pointer calls; NULL = default stream */
 int cfb200_set_stream(void *cuda_stream);
 /* block until the calling thread's stream is idle; returns 0 or -1 */
