@@ -284,11 +284,22 @@ static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, c
   P.scale = scale;
   P.fs = nullptr;
   P.fs_count = 0;
-  if (!batch_fast) {  // row g = m*n1 + k1: scratch rows are contiguous along j2 -> staged load
+  // destination strides of (sequence m, output index k): on peers they come from the PeerOut description
+  const long long d_inc = (po && po->npeers > 0) ? po->elem_inc : oinc, d_jump = (po && po->npeers > 0) ? po->row_jump : ojump;
+  const long long ad_inc = d_inc < 0 ? -d_inc : d_inc, ad_jump = d_jump < 0 ? -d_jump : d_jump;
+  // out of place with the SEQUENCE index as the contiguous axis of the destination (the transposed write of a long 1-D
+  // transform): enumerate the rows sequence-fastest, so that a tile's stores are runs along m instead of stride-d_inc
+  const bool seq_fast_out = !batch_fast && ad_jump < ad_inc && lot >= 32;
+  if (!batch_fast && !seq_fast_out) {  // row g = m*n1 + k1: scratch rows are contiguous along j2 -> staged load
     P.ain = make_addr(1, n2, n, n1);
     P.aout = make_addr((long long)n1 * oinc, oinc, ojump, n1);
     P.in_staged = 1;
     set_tw2(P, tw2, 0, n1);
+  } else if (!batch_fast) {  // row g = k1*lot + m: scratch row (m, k1) at m*n + k1*n2, still contiguous along j2
+    P.ain = make_addr(1, n, n2, lot);
+    P.aout = make_addr((long long)n1 * oinc, ojump, oinc, lot);
+    P.in_staged = 1;
+    set_tw2(P, tw2, 1, n1);
   } else {  // row g = k1*lot + m
     P.ain = make_addr(lot, 1, (long long)n2 * lot, lot);
     P.aout = make_addr((long long)n1 * oinc, ojump, oinc, lot);
@@ -307,7 +318,7 @@ static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, c
     P.peer_shift = sh;
     P.out_base = po->base;
     for (int i = 0; i < po->npeers; ++i) P.peers[i] = po->peers[i];
-    if (!batch_fast) P.aout = make_addr((long long)n1 * po->elem_inc, po->elem_inc, po->row_jump, n1);
+    if (!batch_fast && !seq_fast_out) P.aout = make_addr((long long)n1 * po->elem_inc, po->elem_inc, po->row_jump, n1);
     else P.aout = make_addr((long long)n1 * po->elem_inc, po->row_jump, po->elem_inc, lot);
   }
   return pow2_tile_launch(a2, dir, P);

@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_stream_kernel(cpx *
     cpx a[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) a[i] = land[(size_t)tl * N + t + NT * i];
+    fence_async_smem();  // order the reads of the landing buffer before the bulk engine's next write to it
     __syncthreads();  // the landing buffer has been consumed: refill it with the next tile while we compute
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
@@ -395,6 +396,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
         }
       }
     }
+    fence_async_smem();  // order the reads of the landing buffer before the bulk engine's next write to it
     __syncthreads();
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
@@ -521,11 +523,13 @@ __device__ __forceinline__ void tile_store(const TileParams &P, cpx (&a)[C::P], 
     for (int i = 0; i < PP; ++i) a[i] = ctw<DIR>(a[i], b[i]);
   }
   if (P.tw2) {
-    const long long seq = (P.tw2_seq_lo ? lo : hi) + P.tw2_off, k0 = P.tw2_seq_lo ? hi : lo;
+    const int seq_lo = P.tw2_seq_lo;
+    const long long seq = (seq_lo ? lo : hi) + P.tw2_off, k0 = seq_lo ? hi : lo;
     const long long mask = P.tw2_mask, step = (seq * P.tw2_n1) & mask;
     const long long lmask = (1LL << P.tw2_shift) - 1;
     const int sh = P.tw2_shift;
-    auto root = [&](long long x) { return cmul(__ldg(P.tw2 + (x & lmask)), __ldg(P.tw2 + lmask + 1 + (x >> sh))); };
+    const cpx *tb = P.tw2;
+    auto root = [&](long long x) { return cmul(__ldg(tb + (x & lmask)), __ldg(tb + lmask + 1 + (x >> sh))); };
     const cpx b0 = root((seq * k0 + step * t) & mask), w1 = root((step * NT) & mask), w4 = root((4 * step * NT) & mask);
     cpx b[PP];
 #pragma unroll
@@ -762,6 +766,7 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS <= 128 ? 4 : 2)) pow2_
     cpx a[PP];
 #pragma unroll
     for (int i = 0; i < PP; ++i) a[i] = STAGED ? land[(size_t)tl * TS::LPITCH + t + NT * i] : land[(size_t)(t + NT * i) * TPB + tl];
+    fence_async_smem();  // order this thread's reads of the landing buffer before the bulk engine's next write to it
     __syncthreads();  // landing buffer consumed: refill it while we compute
     const long long next = tile + gridDim.x;
     if (tid < 32 && next < ntiles) issue(next);

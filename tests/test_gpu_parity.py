@@ -126,6 +126,52 @@ def test_long_complex_four_step():
     _check_batched("cfft", "f", 4, 1, 16384, 4)
 
 
+def test_long_power_of_two_1d_beyond_four_step():
+    """cfft1f_/cfft1b_ of 2^21 .. 2^26 points on one GPU (six-step over the four-step sweeps; the reference does any N in
+    core, fftpack.c:2199-2245): full comparison with the CPU oracle up to 2^24, sampled bins against the direct DFT sums
+    of the definition (test/naivepack.c naive_fft) at 2^26, round trips, and run-to-run determinism (the first version
+    of this path exposed a landing-buffer race between shared-memory reads and the next bulk copy)."""
+    torch = _torch()
+    import sys
+    import cfftpack_b200 as cb
+    sys.path.insert(0, fl.ROOT + "/tools")
+    from run_dist1d import dft_bins
+    for a in (21, 22, 23, 24, 26):
+        n = 1 << a
+        g = torch.Generator(device="cuda").manual_seed(a)
+        x0 = torch.view_as_complex(torch.rand(n, 2, generator=g, device="cuda", dtype=torch.float64) - 0.5)
+        plan = cb.Plan("cfft", n)
+        outs = []
+        for rep in range(4):
+            x = x0.clone()
+            assert plan.multi("f", x.data_ptr(), 1, n, 1, n) == 0, cb.last_error()
+            cb.synchronize()
+            outs.append(x)
+        for o in outs[1:]:
+            assert torch.equal(torch.view_as_real(o), torch.view_as_real(outs[0])), (a, "run-to-run difference")
+        x = outs[0]
+        if a <= 24:
+            want, ier = ORC.run1("cfft", "f", n, x0.cpu().numpy())
+            assert fl.rel_l2(x.cpu().numpy(), want) <= fl.tol(n), a
+        else:
+            gen = torch.Generator().manual_seed(3)
+            bins = sorted(set([0, 1, n // 2, n - 1] + torch.randint(0, n, (96,), generator=gen).tolist()))
+            want = dft_bins(x0, 0, n, bins, -1.0, 1) / n
+            rms = float(torch.sqrt((x.abs() ** 2).mean()))
+            assert float((x[torch.tensor(bins, device="cuda")] - want).abs().max()) <= fl.tol(n) * rms, a
+        assert plan.multi("b", x.data_ptr(), 1, n, 1, n) == 0
+        cb.synchronize()
+        back = float((torch.view_as_real(x) - torch.view_as_real(x0)).norm() / torch.view_as_real(x0).norm())
+        assert back <= fl.tol(n), (a, back)
+    # batched and strided long sequences: lot = 3 sequences of 2^21 interleaved (jump = 1, inc = 3)
+    n, lot = 1 << 21, 3
+    xh = fl.rand_input("cfft", n * lot, 5)
+    a_, ia = PROD.runm("cfft", "f", lot, 1, n, lot, xh, work=False)
+    b_, ib = ORC.runm("cfft", "f", lot, 1, n, lot, xh)
+    assert ia == ib == 0
+    assert max(fl.rel_l2(a_[m::lot], b_[m::lot]) for m in range(lot)) <= fl.tol(n)
+
+
 def test_large_prime_factors_chirp_z():
     for n, lot in ((4831, 3), (2 * 4339, 2), (10007, 2), (65537, 1)):
         extra = 2e-15 * np.log2(n)  # the oracle's own O(p^2) sums are the noisier side for primes this large
