@@ -145,8 +145,7 @@ __global__ void __launch_bounds__(W, (W <= 96 ? 4 : W <= 128 ? 3 : 2)) m3_stream
     m3_pass<C::R0, 1, C::NB0, W, CD>(load0, P, tab + C::T0, tab + C::RT0, t);
     // the previous pair's bulk store must have finished reading Q before pass 1 overwrites it
     if (t == 0) bulk_wait_read();
-    fence_async_smem();  // order the reads of the landing buffer before the bulk engine's next write to it
-    __syncthreads();  // landing buffer consumed: refill it with the next pair while this one is transformed
+    __syncthreads();  // landing buffer consumed (pass 0 has turned every read into results stored in P): refill it with the next pair while this one is transformed
     const long long next = tile + gridDim.x;
     if (t == 0 && next < npairs) {
       mbar_expect_tx(bar, PAIR_BYTES);

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_stream_kernel(cpx *
     cpx a[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) a[i] = land[(size_t)tl * N + t + NT * i];
-    fence_async_smem();  // order the reads of the landing buffer before the bulk engine's next write to it
+    landing_reads_done(a, (volatile unsigned *)(bar + 1));
     __syncthreads();  // the landing buffer has been consumed: refill it with the next tile while we compute
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
         }
       }
     }
-    fence_async_smem();  // order the reads of the landing buffer before the bulk engine's next write to it
+    landing_reads_done(a, (volatile unsigned *)(bar + 1));
     __syncthreads();
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS <= 128 ? 4 : 2)) pow2_
     cpx a[PP];
 #pragma unroll
     for (int i = 0; i < PP; ++i) a[i] = STAGED ? land[(size_t)tl * TS::LPITCH + t + NT * i] : land[(size_t)(t + NT * i) * TPB + tl];
-    fence_async_smem();  // order this thread's reads of the landing buffer before the bulk engine's next write to it
+    landing_reads_done(a, (volatile unsigned *)(bar + 1));
     __syncthreads();  // landing buffer consumed: refill it while we compute
     const long long next = tile + gridDim.x;
     if (tid < 32 && next < ntiles) issue(next);

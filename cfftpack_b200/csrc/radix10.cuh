@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(R10Cfg<K>::THREADS, R10Cfg<K>::MINB) r10_c2c_s
     cpx a[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) a[i] = act ? land[(size_t)tl * N + t + NT * i] : make_double2(0.0, 0.0);
-    fence_async_smem();  // order the reads of the landing buffer before the bulk engine's next write to it
+    landing_reads_done(a, (volatile unsigned *)(bar + 1));
     __syncthreads();
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(R10Cfg<K>::THREADS, R10Cfg<K>::MINB) r10_r2c_s
         }
       }
     }
-    fence_async_smem();  // order the reads of the landing buffer before the bulk engine's next write to it
+    landing_reads_done(a, (volatile unsigned *)(bar + 1));
     __syncthreads();
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
@@ -463,7 +463,11 @@ __global__ void __launch_bounds__(R10Cfg<3>::THREADS, R10Cfg<3>::MINB) r10_cost_
       rd[w] = pa;
       rd[NW + w] = pb;
     }
-    fence_async_smem();  // order the reads of the landing buffer before the bulk engine's next write to it
+    {
+      const cpx ends4[2] = {make_double2(x0a, xna), make_double2(x0b, xnb)};
+      landing_reads_done(a, (volatile unsigned *)(bar + 1));
+      landing_reads_done(ends4, (volatile unsigned *)(bar + 1));
+    }
     __syncthreads();  // landing buffer consumed; dsum partials visible
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < ntiles) issue(next);

@@ -158,5 +158,22 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 #endif
 
+/* Handing a landing buffer back to the bulk-copy engine.  The engine writes shared memory through the async proxy and
+ * may overtake ordinary shared-memory reads that are still queued in the SM's memory pipeline when the CTA passes the
+ * barrier that precedes the next bulk copy (observed as rare corrupt tiles).  Every kernel therefore calls this before
+ * that barrier with the registers that were filled from the landing buffer: an integer instruction chain that depends on
+ * all of them feeds a (never taken, harmless) predicated shared-memory store, so the reads have delivered their values
+ * before the barrier -- without the cost of fence.proxy.async, which also drains the previous tile's global stores
+ * (measured: rfftmf 0.82 -> 0.88 ms with the fence).  `spare` is any 4-byte shared-memory word the kernel does not use. */
+template <int P>
+__device__ __forceinline__ void landing_reads_done(const double2 (&a)[P], volatile unsigned *spare) {
+#ifndef CFB_SIM
+  unsigned acc = 0;
+#pragma unroll
+  for (int i = 0; i < P; ++i) acc ^= (unsigned)__double2loint(a[i].x) ^ (unsigned)__double2hiint(a[i].y);
+  if (acc == 0x9e3779b9u) *spare = acc;
+#endif
+}
+
 }  // namespace cfb
 #endif
