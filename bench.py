@@ -510,6 +510,80 @@ def run_cfft2_sharded(args, torch, dist, cb, rank, world, barrier, t1_ms=None):
     return out
 
 
+def run_long1d(args, torch, dist, cb, rank, world, barrier, log2n=28, nbins=64):
+    """one complex transform of 2^log2n points (cfft1f_ semantics), on one GPU through the C ABI
+    (six-step over the four-step sweeps) or in natural order across the GPUs with the exchanges fused into the kernels as
+    P2P stores.  Parity: sampled output bins against the direct O(N) DFT sums of the definition (test/naivepack.c)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from run_dist1d import dft_bins
+    n = 1 << log2n
+    n_loc = n // world
+    g = torch.Generator(device="cuda").manual_seed(11 + rank)
+    x0 = torch.view_as_complex(torch.rand(n_loc, 2, generator=g, device="cuda", dtype=torch.float64) - 0.5)
+    out = {"workload": f"cfft1f 2^{log2n} complex points in natural order over {world} GPU(s)", "n_gpus": world}
+    if world > 1:
+        from cfftpack_b200.dist import Cfft1ShardedP2P
+        plan = Cfft1ShardedP2P(log2n)
+        src = plan.x
+        forward = plan.forward
+        out["exchange"] = "3 exchanges fused into the kernels (P2P stores over NVLink): transpose, twiddled length-Mm pass, length-L pass"
+    else:
+        p1 = cb.Plan("cfft", n)
+        src = x0.clone()
+
+        def forward():
+            ier = p1.multi("f", src.data_ptr(), 1, n, 1, n)
+            if ier != 0:
+                raise RuntimeError(f"cfft1 2^{log2n}: ier={ier}: {cb.last_error()}")
+            return src
+    src.copy_(x0)
+    barrier()
+    y = forward()
+    barrier()
+    gen = torch.Generator().manual_seed(3)
+    bins = sorted(set([0, 1, n // 2, n - 1, n_loc - 1, n_loc % n] + torch.randint(0, n, (nbins,), generator=gen).tolist()))
+    want = dft_bins(x0, rank * n_loc, n, bins, -1.0, world) / n
+    got = torch.zeros(len(bins), 2, device="cuda", dtype=torch.float64)
+    for bi, k in enumerate(bins):
+        if k // n_loc == rank:
+            v = y[k - rank * n_loc]
+            got[bi, 0], got[bi, 1] = v.real, v.imag
+    ms2 = torch.tensor([float((y.abs() ** 2).sum())], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(got)
+        dist.all_reduce(ms2)
+    rms = math.sqrt(float(ms2.item()) / n)
+    err = float((torch.view_as_complex(got) - want).abs().max()) / rms
+    out.update({"parity_max_bin_err_over_rms": err, "parity_bar": 1e-12 * log2n, "parity_ok": bool(err <= 1e-12 * log2n),
+                "parity_sample": f"{len(bins)} output bins vs direct DFT sums over all 2^{log2n} inputs"})
+    src.copy_(x0)
+    steps = max(3, min(args.steps, 5))
+    for _ in range(2):
+        forward()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = cb.launch_count()
+    e0.record()
+    for _ in range(steps):
+        forward()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    link = 3 * 16 * n * (world - 1) // (world * world)
+    out.update({"ms": ms, "steps": steps, "kernels_per_step": int((cb.launch_count() - l0) // steps),
+                "hbm_gbs_algorithmic": 2 * 16 * n / (ms * 1e-3) / 1e9, "gflops_nominal": 5.0 * n * log2n / (ms * 1e-3) / 1e9})
+    if world > 1:
+        out.update({"nvlink_bytes_per_gpu": link, "nvlink_gbs": link / (ms * 1e-3) / 1e9,
+                    "frac_of_900": link / (ms * 1e-3) / 1e9 / NVLINK_GBS, "nvlink_floor_ms": link / (NVLINK_GBS * 1e9) * 1e3})
+    else:
+        peak, _ = hbm_peak()
+        out.update({"sweeps": 4, "frac_per_sweep": 4 * 2 * 16 * n / (ms * 1e-3) / 1e9 / peak})
+    return out
+
+
 def run_cfft2(args, torch, dist, cb, rank, local_rank, world, barrier):
     """--workload cfft2: the cfft2 measurement as the main line (strong scaling)"""
     l = m = args.l2d
@@ -543,15 +617,14 @@ def bind_to_gpu_numa_node(torch, local_rank):
     of the end-to-end leg are first-touched (and therefore placed) next to the GPU's PCIe root instead of all ranks
     sharing node 0.  Best effort: returns a description, never raises."""
     try:
-        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(
-            torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
-        if bdf is None:
-            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                                 capture_output=True, text=True, timeout=10).stdout.strip()
-            bdf = out
-        bdf = bdf.lower()
-        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
-            bdf = bdf[4:]  # sysfs uses a 4-digit PCI domain
+        pr = torch.cuda.get_device_properties(local_rank)
+        if hasattr(pr, "pci_bus_id") and hasattr(pr, "pci_device_id"):
+            bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
+            bdf = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().lower()
+            if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+                bdf = bdf[4:]  # sysfs uses a 4-digit PCI domain
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
         if node < 0:
             return {"numa_node": node, "bound": False}
@@ -690,7 +763,35 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         nbytes = lot * n * esz * 8
+        # ceiling of this leg: the same pinned array copied to the device and back with NO transform, the two directions
+        # on separate streams and in 64 MiB pieces like the library's staging pipeline (PCIe is full duplex)
+        ceil_gbs = None
+        try:
+            dbuf = torch.empty_like(h, device="cuda")
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            pieces = list(zip(h.split(1 << 23), dbuf.split(1 << 23)))
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                for hp, dp in pieces:
+                    with torch.cuda.stream(s_in):
+                        dp.copy_(hp, non_blocking=True)
+                        ev_ = torch.cuda.Event()
+                        ev_.record()
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(ev_)
+                        hp.copy_(dp, non_blocking=True)
+                torch.cuda.synchronize()
+            dtc = (time.perf_counter() - t0) / 2
+            ttc = torch.tensor([dtc], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ttc, op=dist.ReduceOp.MAX)
+            ceil_gbs = world * bytes_rank / float(ttc.item()) / 1e9
+            del dbuf
+        except Exception as ex:
+            ceil_gbs = f"unavailable: {ex}"
         e2e = {"value": world * bytes_rank / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
+               "copy_only_ceiling_gbs": ceil_gbs,
                "d2h_bytes_per_step": nbytes, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
                "note": f"host pinned array -> {fam}mf_ C ABI -> host; copies inside the timed region", "host_numa": numa}
         del h
@@ -737,6 +838,14 @@ def main():
         except Exception as ex:
             cfft2 = {"error": f"{type(ex).__name__}: {ex}"}
 
+    long1d = None
+    if not args.no_cfft2:
+        try:
+            long1d = run_long1d(args, torch, dist, cb, rank, world, barrier)
+        except Exception as ex:
+            long1d = {"error": f"{type(ex).__name__}: {ex}"}
+        torch.cuda.empty_cache()
+
     configs = None
     cpu = None
     if rank == 0:
@@ -758,6 +867,8 @@ def main():
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         if cfft2 is not None:
             out["cfft2"] = cfft2
+        if long1d is not None:
+            out["cfft1_long"] = long1d
         if configs is not None:
             out["configs"] = configs
         print(json.dumps(out), flush=True)

@@ -200,14 +200,87 @@ struct FourStepIO {
   long long inc_out, jump_out;
 };
 static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, const FourStepIO &io, int dir, double scale,
-                                         const PeerOut *po, const Tw2 *tw2);
+                                         const PeerOut *po, const Tw2 *tw2, int sweep = 0, cpx *scr_in = nullptr);
 
 /* Batches much larger than the L2 cache (126 MB) are walked in lot-chunks whose intermediate (the scratch array
  * between the two sweeps) stays L2-resident: sweep 1 of a chunk reads HBM and writes L2, sweep 2 reads L2 and writes
  * HBM, so the whole transform moves each element over the HBM pins once each way instead of twice.
  * CFB200_FS_CHUNK_MB sets the chunk size (0 = one chunk). */
+/* Sharded transforms: the second sweep of a phase is bound by NVLink (its stores go to the peers), the first one by
+ * HBM.  The slab is cut into chunks; sweep 1 of chunk c+1 runs on a second stream while sweep 2 of chunk c drains over
+ * the links, each kernel holding one CTA per SM, with two intermediate buffers.  CFB200_P2P_CHUNKS sets the number of
+ * chunks (default 8; 1 = the two sweeps back to back). */
+struct OverlapStreams {
+  cudaStream_t st[2] = {0, 0};
+  cudaEvent_t ev_start = 0, ev1[16], ev2[16], ev_end[2];
+  int dev = -1;
+  bool ok = false;
+};
+static thread_local OverlapStreams t_ov;
+static bool overlap_ready() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (t_ov.ok && t_ov.dev == dev) return true;
+  if (t_ov.ok) return false;  // one device per host thread for this path
+  for (auto &s : t_ov.st) CFB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  CFB_CUDA(cudaEventCreateWithFlags(&t_ov.ev_start, cudaEventDisableTiming));
+  for (auto &e : t_ov.ev1) CFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : t_ov.ev2) CFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : t_ov.ev_end) CFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  t_ov.dev = dev;
+  t_ov.ok = true;
+  return true;
+}
+
+static bool run_c2c_pow2_four_step_pipelined(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c,
+                                             double scale, const PeerOut *po, const Tw2 *tw2, int chunks) {
+  long long per = (lot + chunks - 1) / chunks;
+  per = (per + 255) / 256 * 256;
+  const int nch = (int)((lot + per - 1) / per);
+  if (nch < 2 || nch > 16 || !overlap_ready()) return false;
+  cudaStream_t user = current_stream();
+  cpx *scr = (cpx *)scratch_get(0, (size_t)2 * per * n * sizeof(cpx));
+  if (!scr || !get_root_plan(n)) return false;
+  bool ok = cuda_ok(cudaEventRecord(t_ov.ev_start, user), "cudaEventRecord");
+  for (int k = 0; k < 2 && ok; ++k) ok = cuda_ok(cudaStreamWaitEvent(t_ov.st[k], t_ov.ev_start, 0), "cudaStreamWaitEvent");
+  set_tile_cta_cap(1);
+  for (int ch = 0; ch < nch && ok; ++ch) {
+    const long long m0 = (long long)ch * per, lc = lot - m0 < per ? lot - m0 : per;
+    PeerOut sub = *po;
+    sub.base += m0 * po->row_jump;
+    Tw2 t2;
+    if (tw2) {
+      t2 = *tw2;
+      t2.off += m0;
+    }
+    const FourStepIO io = {c + m0 * jump, inc, jump, c + m0 * jump, inc, jump};
+    cpx *buf = scr + (size_t)(ch & 1) * per * n;
+    // sweep 1 (HBM bound) on stream 0; its buffer was last read by sweep 2 of chunk ch - 2
+    set_current_stream(t_ov.st[0]);
+    if (ch >= 2) ok = cuda_ok(cudaStreamWaitEvent(t_ov.st[0], t_ov.ev2[ch - 2], 0), "cudaStreamWaitEvent");
+    ok = ok && run_c2c_pow2_four_step_chunk(n, a1, a2, lc, io, dir, scale, &sub, tw2 ? &t2 : nullptr, 1, buf) &&
+         cuda_ok(cudaEventRecord(t_ov.ev1[ch], t_ov.st[0]), "cudaEventRecord");
+    // sweep 2 (NVLink bound) on stream 1
+    set_current_stream(t_ov.st[1]);
+    ok = ok && cuda_ok(cudaStreamWaitEvent(t_ov.st[1], t_ov.ev1[ch], 0), "cudaStreamWaitEvent") &&
+         run_c2c_pow2_four_step_chunk(n, a1, a2, lc, io, dir, scale, &sub, tw2 ? &t2 : nullptr, 2, buf) &&
+         cuda_ok(cudaEventRecord(t_ov.ev2[ch], t_ov.st[1]), "cudaEventRecord");
+  }
+  set_tile_cta_cap(0);
+  set_current_stream(user);
+  for (int k = 0; k < 2; ++k)
+    ok = cuda_ok(cudaEventRecord(t_ov.ev_end[k], t_ov.st[k]), "cudaEventRecord") &&
+         cuda_ok(cudaStreamWaitEvent(user, t_ov.ev_end[k], 0), "cudaStreamWaitEvent") && ok;
+  return ok;
+}
+
 static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long long inc, long long jump, int dir, cpx *c,
                                    double scale, const PeerOut *po = nullptr, const Tw2 *tw2 = nullptr) {
+  if (po && po->npeers > 1) {
+    static const int chunks = getenv("CFB200_P2P_CHUNKS") ? atoi(getenv("CFB200_P2P_CHUNKS")) : 8;
+    if (chunks > 1 && lot >= 512 && run_c2c_pow2_four_step_pipelined(n, a1, a2, lot, inc, jump, dir, c, scale, po, tw2, chunks))
+      return true;
+  }
   static const long long chunk_mb = getenv("CFB200_FS_CHUNK_MB") ? atoll(getenv("CFB200_FS_CHUNK_MB")) : 0;
   long long per = chunk_mb > 0 ? (chunk_mb << 20) / ((long long)n * (long long)sizeof(cpx)) : lot;
   per -= per % 256;  // whole tiles of every row length the sweeps use
@@ -243,14 +316,16 @@ static void set_tw2(TileParams &P, const Tw2 *tw2, int seq_lo, int n1) {
   P.tw2_n1 = n1;
 }
 
+/* sweep = 1, 2: only that sweep (the pipelined sharded path issues them on different streams); 0: both.  scr_in: the
+ * intermediate array to use (nullptr: the thread's scratch slot 0) */
 static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, const FourStepIO &io, int dir, double scale,
-                                         const PeerOut *po, const Tw2 *tw2) {
+                                         const PeerOut *po, const Tw2 *tw2, int sweep, cpx *scr_in) {
   const long long inc = io.inc, jump = io.jump;
   const cpx *c = io.cin;
   const int n1 = 1 << a1, n2 = 1 << a2;
   const RootPlan *rp = get_root_plan(n);
   if (!rp) return false;
-  cpx *scr = (cpx *)scratch_get(0, (size_t)lot * n * sizeof(cpx));
+  cpx *scr = scr_in ? scr_in : (cpx *)scratch_get(0, (size_t)lot * n * sizeof(cpx));
   if (!scr) return false;
   const long long ainc = inc < 0 ? -inc : inc, ajump = jump < 0 ? -jump : jump;
   const bool batch_fast = ajump < ainc && lot > 1;
@@ -275,7 +350,8 @@ static bool run_c2c_pow2_four_step_chunk(int n, int a1, int a2, long long lot, c
     P.fs_from_hi = 1;
   }
   P.in_staged = 0;
-  if (!pow2_tile_launch(a1, dir, P)) return false;
+  if (sweep != 2 && !pow2_tile_launch(a1, dir, P)) return false;
+  if (sweep == 1) return true;
   // step 2: rows (m, k1), transform over j2 (length n2), output element k2 goes to index k1 + n1*k2
   const long long oinc = io.inc_out, ojump = io.jump_out;
   P.in = scr;

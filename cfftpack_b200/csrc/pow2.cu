@@ -159,6 +159,7 @@ bool launch_tile_stream(TileParams &P) {
   const long long ntiles = (P.lot + C::TPB - 1) / C::TPB;
   long long per_sm = (long long)((SMEM_LIMIT + 1024) / (smem + 1024));
   if (per_sm > (C::THREADS > 256 ? 1 : 2)) per_sm = (C::THREADS > 256 ? 1 : 2);
+  if (tile_cta_cap() > 0 && per_sm > tile_cta_cap()) per_sm = tile_cta_cap();
   if (per_sm < 1) per_sm = 1;
   long long grid = per_sm * sm_count();
   if (grid > ntiles) grid = ntiles;
@@ -189,6 +190,7 @@ bool launch_tile_tma(TileParams &P, bool *declined) {  // *declined: the tensor 
   long long per_sm = (long long)((SMEM_LIMIT + 1024) / (smem + 1024));
   const long long reg_cap = C::THREADS <= 128 ? 4 : 2;
   if (per_sm > reg_cap) per_sm = reg_cap;
+  if (tile_cta_cap() > 0 && per_sm > tile_cta_cap()) per_sm = tile_cta_cap();
   if (per_sm < 1) per_sm = 1;
   long long grid = per_sm * sm_count();
   if (grid > ntiles) grid = ntiles;
