@@ -13,7 +13,10 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/cfftpack_b200.h"
@@ -285,10 +288,73 @@ struct PipeStreams {
 };
 static thread_local PipeStreams t_pipe;
 
+/* ---- several GPUs behind one C call (host arrays of batched transforms): the lot axis is cut into one contiguous
+ * shard per device (independent sequences, no exchange) and each shard is staged and transformed by a
+ * persistent worker thread bound to its device.  Everything a transform needs (stream, scratch, plans, kernel attributes,
+ * SM count) is already keyed per host thread and device, so the workers run the ordinary single-GPU path.
+ * Off unless asked for: cfb200_set_devices(n) or CFB200_DEVICES=n|all (one process per GPU under torchrun must not fan out). */
+struct DevicePool {
+  struct Worker {
+    std::thread th;
+    std::function<bool()> job;
+    bool has_job = false, result = true, quit = false;
+    char err[512] = "";
+  };
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  std::vector<Worker *> workers;  // worker i serves device i + 1 (device 0 is the calling thread's share)
+  int pending = 0;
+  void ensure(int n) {
+    std::lock_guard<std::mutex> lk(mu);
+    while ((int)workers.size() < n) {
+      Worker *w = new Worker();
+      const int dev = (int)workers.size() + 1;
+      workers.push_back(w);
+      w->th = std::thread([this, w, dev] {
+        cudaSetDevice(dev);
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+          cv_job.wait(lk, [w] { return w->has_job || w->quit; });
+          if (w->quit) return;
+          auto job = w->job;
+          lk.unlock();
+          t_err[0] = 0;
+          const bool ok = job();
+          lk.lock();
+          w->result = ok;
+          snprintf(w->err, sizeof(w->err), "%s", t_err);
+          w->has_job = false;
+          if (--pending == 0) cv_done.notify_all();
+        }
+      });
+      w->th.detach();  // lives for the life of the process
+    }
+  }
+};
+// never destroyed: the detached workers wait on its condition variable for the life of the process, and destroying a
+// condition variable with waiters (static destruction at exit) blocks forever
+static DevicePool &g_pool = *new DevicePool();
+static std::atomic<int> g_devices{0};  // 0 = not decided yet
+static int devices_in_use() {
+  int d = g_devices.load();
+  if (d > 0) return d;
+  d = 1;
+  if (const char *e = getenv("CFB200_DEVICES")) {
+    int n = 0;
+    cudaGetDeviceCount(&n);
+    d = (!strcmp(e, "all") || atoi(e) > n) ? n : atoi(e);
+    if (d < 1) d = 1;
+  }
+  g_devices.store(d);
+  return d;
+}
+
+template <class F>
+static bool run_on_array_one(void *user, size_t esz, long long lot, long long jump, int n, long long inc, F &&fn, int mem_type);
+
 template <class F>
 static bool run_on_array(void *user, size_t esz, long long lot, long long jump, int n, long long inc, F &&fn) {
   const long long seq_span = inc * (long long)(n - 1) + 1;
-  const size_t total = (size_t)((lot - 1) * jump + seq_span) * esz;
   if (!device_ready()) return false;
   cudaPointerAttributes at;
   memset(&at, 0, sizeof(at));
@@ -297,6 +363,42 @@ static bool run_on_array(void *user, size_t esz, long long lot, long long jump, 
     at.type = cudaMemoryTypeUnregistered;
   }
   if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return fn(user, lot);
+  const int G = devices_in_use();
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (G <= 1 || cur != 0 || lot < 2 * G || jump < seq_span)
+    return run_on_array_one(user, esz, lot, jump, n, inc, fn, (int)at.type);
+  // fan out: shard g = sequences [lot g / G, lot (g+1) / G)
+  g_pool.ensure(G - 1);
+  {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    g_pool.pending = G - 1;
+    for (int g = 1; g < G; ++g) {
+      const long long m0 = lot * g / G, m1 = lot * (g + 1) / G;
+      char *p = (char *)user + (size_t)m0 * jump * esz;
+      DevicePool::Worker *w = g_pool.workers[g - 1];
+      w->job = [=, &fn] { return run_on_array_one(p, esz, m1 - m0, jump, n, inc, fn, (int)at.type); };
+      w->has_job = true;
+    }
+  }
+  g_pool.cv_job.notify_all();
+  bool ok = run_on_array_one(user, esz, lot / G, jump, n, inc, fn, (int)at.type);
+  std::unique_lock<std::mutex> lk(g_pool.mu);
+  g_pool.cv_done.wait(lk, [] { return g_pool.pending == 0; });
+  for (int g = 1; g < G; ++g)
+    if (!g_pool.workers[g - 1]->result) {
+      ok = false;
+      set_error("device %d: %s", g, g_pool.workers[g - 1]->err);
+    }
+  return ok;
+}
+
+template <class F>
+static bool run_on_array_one(void *user, size_t esz, long long lot, long long jump, int n, long long inc, F &&fn, int mem_type) {
+  const long long seq_span = inc * (long long)(n - 1) + 1;
+  const size_t total = (size_t)((lot - 1) * jump + seq_span) * esz;
+  cudaPointerAttributes at;
+  at.type = (cudaMemoryType)mem_type;
   static const size_t CHUNK = [] {  // bytes per pipeline stage; CFB200_PIPE_CHUNK_KB overrides (tests)
     const char *e = getenv("CFB200_PIPE_CHUNK_KB");
     return e ? (size_t)atoll(e) << 10 : (size_t)64 << 20;
@@ -644,6 +746,25 @@ int cfb200_cfft1_sharded_phase(int phase, int direction, int log2n, int rank, in
   }
   if (!device_ready() || !run_c2c_1d_sharded_phase(phase, direction < 0 ? -1 : +1, log2n, rank, nranks, local_src, peer_dst)) *ier = -1;
   return 0;
+}
+
+void *cfb200_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (!device_ready() || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void cfb200_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int cfb200_set_devices(int n) {
+  int have = 0;
+  if (!device_ready() || cudaGetDeviceCount(&have) != cudaSuccess || have < 1) return 0;
+  g_devices.store(n <= 0 || n > have ? have : n);
+  return g_devices.load();
 }
 
 int cfb200_set_stream(void *s) {

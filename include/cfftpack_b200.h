@@ -110,6 +110,17 @@ int cfb200_cfft2_sharded_phase(int phase, int direction, int l, int m, int rank,
  * direction < 0.  ier as for cfb200_cfft2_sharded_phase. */
 int cfb200_cfft1_sharded_phase(int phase, int direction, int log2n, int rank, int nranks, void *local_src,
                                void *const *peer_dst, int *ier);
+/* Number of GPUs (devices 0 .. n-1 of this process) that batched calls on HOST arrays -- cfftmf_/cfftmb_, rfftm*, costm*,
+ * sintm*, cosqm*, sinqm* (cfftpack/fftpack.c:2554, :14035, ...) -- fan out over: the lot axis is cut into one contiguous
+ * shard per GPU, each staged and transformed concurrently (no exchange: the sequences are independent).
+ * n <= 0: all visible devices.  Default 1, or the environment variable CFB200_DEVICES (a number or "all").  Applies
+ * when the calling thread's current device is 0 and the sequences do not interleave (jump >= span of one sequence).
+ * Returns the number now in effect (0 without a CUDA device). */
+int cfb200_set_devices(int n);
+/* Page-locked host memory, usable from every GPU of the process: arrays allocated here are staged by DMA at full PCIe
+ * rate (and in overlapping lot-chunks); ordinary malloc'ed arrays work too, through the driver's bounce buffers. */
+void *cfb200_host_alloc(size_t bytes);
+void cfb200_host_free(void *p);
 /* CUDA stream (cudaStream_t) used by THIS host thread for device-pointer calls; NULL = default stream */
 int cfb200_set_stream(void *cuda_stream);
 /* block until the calling thread's stream is idle; returns 0 or -1 */

@@ -655,6 +655,44 @@ def test_reference_option_pricing_demo_relinked():
     assert abs(vg_last - 9.3424659413582116) < 2e-5
 
 
+def test_host_array_fans_out_over_gpus_from_the_c_boundary():
+    """needs >= 2 GPUs (skipped otherwise): with CFB200_DEVICES=2 one cfftmf_/rfftmf_/cosqmf_ call on a host array is
+    sharded by lot over both GPUs inside the library (worker threads); results equal the single-GPU path."""
+    import os
+    import subprocess
+    import sys
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("single GPU")
+    code = r"""
+import sys, ctypes, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import cfftpack_b200 as cb
+import fftlibs as fl
+ORC = fl.Lib(fl.oracle(), "orc_")
+assert cb.lib.cfb200_set_devices(0) >= 2
+bad = 0
+for fam, n, lot in (("cfft", 4096, 3001), ("rfft", 4096, 5000), ("cosq", 1001, 4001), ("cfft", 360, 7), ("sint", 1000, 2048)):
+    esz = 2 if fam == "cfft" else 1
+    h = torch.empty(lot * n * esz, dtype=torch.float64, pin_memory=True).uniform_(-1, 1)
+    x0 = h.clone().numpy()
+    plan = cb.Plan(fam, n)
+    assert plan.multi("f", h.data_ptr(), lot, n, 1, lot * n) == 0, cb.last_error()
+    got = h.numpy()
+    rows = sorted(set([0, 1, lot // 2 - 1, lot // 2, lot // 2 + 1, lot - 2, lot - 1]))
+    for r in rows:
+        a = x0[r * n * esz:(r + 1) * n * esz]; b = got[r * n * esz:(r + 1) * n * esz]
+        if fam == "cfft": a, b = a.view(np.complex128), b.view(np.complex128)
+        want, ier = ORC.run1(fam, "f", n, a)
+        if fl.rel_l2(b, want) > fl.tol(n):
+            bad += 1; print("MISMATCH", fam, n, lot, r, fl.rel_l2(b, want))
+print("BAD", bad)
+sys.exit(1 if bad else 0)
+""" % (fl.ROOT, fl.ROOT + "/tests")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-2000:])
+
+
 def test_sharded_cfft2_two_gpus_fused_p2p_vs_nccl():
     """needs >= 2 GPUs (skipped on single-GPU boxes): the FFT+transpose fused path (P2P stores into peer slabs) must
     agree with the NCCL all-to-all path (bit for bit only when both pick the same factorisation, e.g. at 16384) and
