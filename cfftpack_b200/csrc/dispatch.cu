@@ -17,7 +17,7 @@
 #include "plan.h"
 #include "pow2.cuh"
 #include "radix10.cuh"
-#include "mixed3.cuh"
+#include "mixed.cuh"
 
 namespace cfb {
 
@@ -876,6 +876,23 @@ bool run_real(int kind, int n, long long lot, long long inc, long long jump, int
     count_launch();
     return cuda_ok(cudaGetLastError(), "tiny_kernel launch");
   }
+  // A/B switch: CFB200_NO_MIX=1 the older kernels everywhere, =2 only for M = 1000 (radix10.cuh)
+  static const int no_mix = getenv("CFB200_NO_MIX") ? atoi(getenv("CFB200_NO_MIX")) : 0;
+  const int Mu = kind == K_COST ? n - 1 : kind == K_SINT ? n + 1 : n;
+  if (no_mix != 1 && !(no_mix == 2 && Mu == 1000) && mix_supported(kind, n) && inc == 1 && jump == n && lot >= 2 &&
+      (((uintptr_t)x) & 15) == 0) {
+    // mixed-radix streaming kernel on the pairs of rows; a last odd row goes through the general engine
+    const double *trig = nullptr;
+    if (kind != K_RFFT) {
+      const TrigPlan *tp = get_trig_plan(kind, n);
+      if (!tp) return false;
+      trig = tp->d_trig;
+    }
+    if (!mix_launch(kind, n, lot / 2, dir, x, trig)) return false;
+    if (lot % 2 == 0) return true;
+    x += (lot - 1) * jump;
+    lot = 1;
+  }
   if (kind == K_RFFT && pow2_r2c_supported(n, inc, jump, (((uintptr_t)x) & 15) == 0))
     return pow2_r2c_launch(n, lot, jump, dir, x);
   if (kind == K_RFFT && r10_supported(n) && inc == 1 && jump >= n && jump % 2 == 0 && (((uintptr_t)x) & 15) == 0)
@@ -890,20 +907,6 @@ bool run_real(int kind, int n, long long lot, long long inc, long long jump, int
     const TrigPlan *tp = get_trig_plan(K_COST, n);
     if (!tp) return false;
     if (!r10_cost_launch(lot / 2, dir, x, tp->d_trig)) return false;
-    if (lot % 2 == 0) return true;
-    x += (lot - 1) * jump;
-    lot = 1;
-  }
-  static const bool no_m3 = getenv("CFB200_NO_M3") != nullptr;  // A/B switch: the general engine instead
-  if (!no_m3 && m3_supported(kind, n) && inc == 1 && jump == n && lot >= 2 && (((uintptr_t)x) & 15) == 0) {
-    // 13*11*7 register kernel on the pairs of rows; a last odd row goes through the general engine
-    const double *trig = nullptr;
-    if (kind != K_RFFT) {
-      const TrigPlan *tp = get_trig_plan(kind, n);
-      if (!tp) return false;
-      trig = tp->d_trig;
-    }
-    if (!m3_launch(kind, n, lot / 2, dir, x, trig)) return false;
     if (lot % 2 == 0) return true;
     x += (lot - 1) * jump;
     lot = 1;

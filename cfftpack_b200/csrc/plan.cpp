@@ -297,14 +297,14 @@ const ChirpPlan *get_chirp_plan(int n) {
 
 void pow2_release_tables();
 void r10_release_tables();
-void m3_release_tables();
+void mix_release_tables();
 
 /* The caller must be quiescent: no other host thread inside a transform (plans are handed out as raw pointers). */
 void release_plans() {
   cudaDeviceSynchronize();  // kernels in flight may still read the tables
   pow2_release_tables();
   r10_release_tables();
-  m3_release_tables();
+  mix_release_tables();
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto &kv : g_core) {
     cudaFree(kv.second->d_tw);
