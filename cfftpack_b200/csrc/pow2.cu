@@ -114,11 +114,18 @@ bool launch_c2c_stream(long long lot, long long jump, cpx *c, double scale) {
   return cuda_ok(cudaGetLastError(), "pow2_c2c_stream_kernel launch");
 }
 
+template <class C, int MINB, int DIR, bool BULK>
+bool launch_r2c_stream_v(long long lot, long long jump, double *r);
 template <class C, int MINB, int DIR>
 bool launch_r2c_stream(long long lot, long long jump, double *r) {
+  static const int bulk = getenv("CFB200_R2C_BULK") ? atoi(getenv("CFB200_R2C_BULK")) : 1;  // 0: per-thread stores (A/B)
+  return bulk ? launch_r2c_stream_v<C, MINB, DIR, true>(lot, jump, r) : launch_r2c_stream_v<C, MINB, DIR, false>(lot, jump, r);
+}
+template <class C, int MINB, int DIR, bool BULK>
+bool launch_r2c_stream_v(long long lot, long long jump, double *r) {
   const cpx *tw = pow2_stream_table<C>();
   if (!tw) return false;
-  auto kern = pow2_r2c_stream_kernel<C, MINB, DIR>;
+  auto kern = pow2_r2c_stream_kernel<C, MINB, DIR, BULK>;
   if (!set_smem_once(kern, StreamSmem<C>::BYTES)) return false;
   const long long pairs = (lot + 1) / 2;
   const long long ntiles = (pairs + C::TPB - 1) / C::TPB;

@@ -349,7 +349,10 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_stream_kernel(cpx *
 }
 
 /* real pairs, streaming: the landing buffer holds the two rows x_a, x_b of each pair back to back */
-template <class C, int MINB, int DIR>
+/* BULK: finished rows are written into the (then idle) exchange tile in their final layout and drained by one
+ * cp.async.bulk shared->global per row instead of per-thread global stores (the split epilogue with its lane shuffles and
+ * divergent edge stores was 34 % of the kernel's stall samples, profiles/r2_ncu_r2c4096.txt) */
+template <class C, int MINB, int DIR, bool BULK = false>
 __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(double *__restrict__ r, long long lot,
                                                                            long long jump, const cpx *__restrict__ tw,
                                                                            long long ntiles) {
@@ -397,6 +400,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
       }
     }
     landing_reads_done(a, (volatile unsigned *)(bar + 1));
+    if (BULK && t == 0) bulk_wait_read();  // the previous tile's rows have left the exchange tile
     __syncthreads();
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
@@ -412,6 +416,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
       // next lane by shuffle, so that all but the warp-edge lanes issue full 16-byte stores.
       const double sc = 1.0 / (double)N;
       const int lane = tid & 31;
+      cpx nyq = make_double2(0.0, 0.0);
       // three passes over the 8 slots so that the shared-memory loads, the arithmetic and the shuffles of different
       // slots overlap (one fused loop exposed each latency 8 times: 39 % of the stall samples, profiles/r1_ncu_r2c_src.txt).
       // The upper half of a[] is free after the exchange: it receives the partners, then the results of row b.
@@ -425,14 +430,42 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
         const int f = t + NT * i;
         const cpx u = a[i], v = a[P / 2 + i];
         if (f == 0) {  // slot 0 holds X0 itself; A_{N/2} = X_{N/2} / N closes the row
-          if (va) xa[N - 1] = v.x * sc;
-          if (vb) xb[N - 1] = v.y * sc;
+          nyq = make_double2(v.x * sc, v.y * sc);
+          if (!BULK && va) xa[N - 1] = v.x * sc;
+          if (!BULK && vb) xb[N - 1] = v.y * sc;
           a[i] = make_double2(0.0, u.x * sc);
           a[P / 2 + i] = make_double2(0.0, u.y * sc);
         } else {
           a[i] = make_double2((u.x + v.x) * sc, (v.y - u.y) * sc);          // (A, B) of row a
           a[P / 2 + i] = make_double2((u.y + v.y) * sc, (u.x - v.x) * sc);  // (A, B) of row b
         }
+      }
+      if (BULK) {
+        // a[i] = (A_f, B_f) of row a, a[P/2 + i] of row b (slot f = 0: (-, X0/N); X_{N/2}/N already stored below)
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+          // row 0: every partner read of zq is done.  row 1: thread 0 gets here only after the bulk engine has read row 0.
+          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < P / 2; ++i) {
+            const int f = t + NT * i;
+            const cpx ab = a[row * (P / 2) + i];
+            if (f == 0) xq[0] = ab.y;
+            else {
+              xq[2 * f - 1] = ab.x;
+              xq[2 * f] = ab.y;
+            }
+          }
+          if (t == 0) xq[N - 1] = row == 0 ? nyq.x : nyq.y;
+          fence_async_smem();
+          __syncthreads();
+          if (t == 0 && (row == 0 ? va : vb)) {
+            bulk_s2g(row == 0 ? xa : xb, xq, (unsigned)(N * sizeof(double)));
+            bulk_commit();
+            if (row == 0) bulk_wait_read();  // the tile is reused for row b right away
+          }
+        }
+        continue;
       }
 #pragma unroll
       for (int i = 0; i < P / 2; ++i) {
@@ -453,6 +486,23 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
       }
       // no barrier needed here: the next tile's first write to this exchange tile comes after its landing-read barrier,
       // which every thread only reaches once it has finished reading zq above
+    } else if (BULK) {
+      // pow2_core_split ends with a barrier after its last exchange read: the tile is free
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        if (row == 1) {
+          if (t == 0 && va) bulk_wait_read();
+          __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) xq[t + NT * i] = row == 0 ? a[i].x : a[i].y;
+        fence_async_smem();
+        __syncthreads();
+        if (t == 0 && (row == 0 ? va : vb)) {
+          bulk_s2g(row == 0 ? xa : xb, xq, (unsigned)(N * sizeof(double)));
+          bulk_commit();
+        }
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < P; ++i) {
@@ -461,6 +511,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
       }
     }
   }
+  if (BULK && t == 0) bulk_wait_all();
 }
 
 /* ---------------------------------------------------------------------------------------------------------
