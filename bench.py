@@ -443,6 +443,20 @@ def cfft2_parity(torch, dist, x_in, y_out, l, m, rank, world, samples=32):
     return float(t.item()), len(cols), len(rows)
 
 
+def nvlink_tx_kib(index):
+    """sum over the links of GPU `index` of the NVLink data-transmit counter (KiB), or None (nvidia-smi nvlink -gt d)"""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        tot, seen = 0, False
+        for ln in out.splitlines():
+            if "Data Tx" in ln:
+                tot += int(ln.split(":")[-1].strip().split()[0])
+                seen = True
+        return tot if seen else None
+    except Exception:
+        return None
+
+
 def run_cfft2_sharded(args, torch, dist, cb, rank, world, barrier, t1_ms=None):
     """sharded cfft2f l x l over `world` GPUs (strong scaling); returns the `cfft2` object of the JSON line"""
     from cfftpack_b200.dist import Cfft2Sharded, Cfft2ShardedP2P
@@ -485,17 +499,22 @@ def run_cfft2_sharded(args, torch, dist, cb, rank, world, barrier, t1_ms=None):
     barrier()
     l0 = cb.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tx0 = nvlink_tx_kib(torch.cuda.current_device()) if rank == 0 else None
     barrier()
     e0.record()
     for _ in range(steps):
         forward()
     e1.record()
     barrier()
+    tx1 = nvlink_tx_kib(torch.cuda.current_device()) if rank == 0 else None
     t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     link_bytes_one = 16 * l * m * (world - 1) // (world * world)  # per GPU per exchange
+    if tx0 is not None and tx1 is not None:
+        out["nvlink_tx_bytes_per_step_counted"] = (tx1 - tx0) * 1024 // steps
+        out["nvlink_counter_source"] = "nvidia-smi nvlink -gt d on rank 0's GPU, before and after the timed loop (includes barrier traffic)"
     out.update({"ms": ms, "steps": steps, "kernels_per_step": int((cb.launch_count() - l0) // steps),
                 "hbm_gbs_2pass_minimum": 2 * 2 * 16 * l * m / (ms * 1e-3) / 1e9,
                 "gflops_nominal": 5.0 * l * m * math.log2(l * m) / (ms * 1e-3) / 1e9,

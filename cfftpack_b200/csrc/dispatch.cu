@@ -283,8 +283,8 @@ static bool run_c2c_pow2_four_step(int n, int a1, int a2, long long lot, long lo
   }
   static const long long chunk_mb = getenv("CFB200_FS_CHUNK_MB") ? atoll(getenv("CFB200_FS_CHUNK_MB")) : 0;
   long long per = chunk_mb > 0 ? (chunk_mb << 20) / ((long long)n * (long long)sizeof(cpx)) : lot;
-  per -= per % 256;  // whole tiles of every row length the sweeps use
-  if (per < 256 || per >= lot) {
+  per -= per % 64;  // whole tiles of the row lengths the sweeps use
+  if (per < 64 || per >= lot) {
     const FourStepIO io = {c, inc, jump, c, inc, jump};
     return run_c2c_pow2_four_step_chunk(n, a1, a2, lot, io, dir, scale, po, tw2);
   }

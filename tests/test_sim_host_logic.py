@@ -158,18 +158,68 @@ def test_l2_object_api(libs):
     fl.l2_batch_check(fl.sim())
 
 
-def test_half_length_real_kernel_experiment():
-    """CFB200_R2C_HALF selects the single-row half-length kernel; env is read once per process"""
+def test_rfft_stream_kernel_both_output_paths():
+    """CFB200_R2C_BULK=0 keeps the per-thread global stores of the real stream kernel, the default drains finished rows
+    with bulk shared->global copies; env is read once per process, hence the subprocesses"""
     import subprocess
     import sys
     code = ("import sys; sys.path.insert(0, %r); import fftlibs as fl; "
             "S = fl.Lib(fl.sim()); O = fl.Lib(fl.oracle(), 'orc_'); "
             "x = fl.rand_input('rfft', 3 * 4102, 5); "
             "r = [fl.rel_l2(S.runm('rfft', d, 3, 4102, 4096, 1, x)[0], O.runm('rfft', d, 3, 4102, 4096, 1, x)[0]) for d in 'fb']; "
+            "y = fl.rand_input('rfft', 5 * 256, 6); "
+            "r += [fl.rel_l2(S.runm('rfft', d, 5, 256, 256, 1, y)[0], O.runm('rfft', d, 5, 256, 256, 1, y)[0]) for d in 'fb']; "
             "assert max(r) < 1e-14, r" % os.path.dirname(os.path.abspath(__file__)))
-    for v in ("1", "2"):
-        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CFB200_R2C_HALF=v), capture_output=True, text=True)
+    for v in ("0", "1"):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CFB200_R2C_BULK=v), capture_output=True, text=True)
         assert out.returncode == 0, out.stderr[-2000:]
+
+
+def _device_batch(S, O, fam, d, lot, n, seed):
+    """contiguous, 16-byte aligned batch marked as DEVICE memory, so that the aligned fast paths (bulk copies) are taken"""
+    import ctypes
+    lib = S.lib
+    lib.cfb200_sim_mark_device.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    x = fl.rand_input(fam, n * lot, seed)
+    buf = np.zeros(n * lot + 2)
+    off = (16 - buf.ctypes.data % 16) % 16 // 8
+    y = buf[off:off + n * lot]
+    y[:] = x
+    lib.cfb200_sim_mark_device(ctypes.c_void_p(y.ctypes.data), y.nbytes)
+    ws, _ = S.init(fam, n, multi=True)
+    ier, I = ctypes.c_int(-1), ctypes.c_int
+    getattr(lib, fam + "m" + d + "_")(ctypes.byref(I(lot)), ctypes.byref(I(n)), ctypes.byref(I(n)), ctypes.byref(I(1)), fl.P(y),
+                                      ctypes.byref(I(n * lot)), fl.P(ws), ctypes.byref(I(fl.lensav(fam, n))), fl.P(np.zeros(8)),
+                                      ctypes.byref(I(fl.lenwrk(fam, n, lot))), ctypes.byref(ier))
+    want, ib = O.runm(fam, d, lot, n, n, 1, x)
+    assert ier.value == 0 and ib == 0, (fam, d, n, ier.value, ib)
+    return max(fl.rel_l2(y[i * n:(i + 1) * n], want[i * n:(i + 1) * n]) for i in range(lot)), buf
+
+
+def test_mixed_radix_stream_kernel_all_families_and_lengths(libs):
+    """mixed.cuh: underlying real lengths 999 = 9*3*37, 1000 = 10^3, 1001 = 13*11*7, 1002 = 6*167 (even and odd, register and
+    generic last pass) for rfft / cosq / sint / cost, both directions, even and odd lots (the odd row takes the engine)"""
+    S, O = libs
+    for M in (999, 1000, 1001, 1002):
+        for fam, n in (("rfft", M), ("cosq", M), ("sint", M - 1), ("cost", M + 1)):
+            for d in "fb":
+                for lot in (2, 3):
+                    before = S.lib.cfb200_launch_count()
+                    err, _ = _device_batch(S, O, fam, d, lot, n, 7 * n + lot)
+                    assert err <= fl.tol(n), (fam, d, n, lot, err)
+                    assert S.lib.cfb200_launch_count() - before == (1 if lot % 2 == 0 else 2), (fam, n, lot)
+
+
+def test_long_power_of_two_beyond_the_four_step(libs):
+    """2^21 points: six-step over one tile sweep and a four-step pair (dispatch.cu run_c2c_long_pow2)"""
+    S, O = libs
+    n = 1 << 21
+    x = fl.rand_input("cfft", n, 3)
+    for d in "fb":
+        a, ia = S.run1("cfft", d, n, x)
+        b, ib = O.run1("cfft", d, n, x)
+        assert ia == ib == 0
+        assert fl.rel_l2(a, b) <= fl.tol(n), d
 
 
 def test_pipelined_host_staging(libs):
