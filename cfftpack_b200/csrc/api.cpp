@@ -496,6 +496,141 @@ static int complex_multi(int *lot, int *jump, int *n, int *inc, void *c, int *le
   return 0;
 }
 
+/* ---- cfft2f_/cfft2b_ on a HOST array over several GPUs of this process (cfb200_set_devices / CFB200_DEVICES): column
+ * slabs, one per device, copied in concurrently; the two dimension sweeps are the fused-transpose phases of the sharded
+ * transform (run_c2c_2d_sharded_phase: the last pass of each dimension stores into the peers' slabs over NVLink), with
+ * event barriers between the phases; slabs copied back.  One host thread drives all devices (every launch is
+ * asynchronous).  Needs l = ldim, power-of-two l and m in 2^12..2^20 divisible by the device count, peer access. */
+#ifdef CFB_SIM
+static bool multi2d_eligible(int, int, int, void *) { return false; }
+static bool complex_2d_multi(int, int, void *, int) { return false; }
+static void multi2d_release() {}
+#else
+struct Multi2d {
+  int l = 0, m = 0, G = 0;
+  cudaStream_t st[16];
+  cudaEvent_t ev[16];
+  void *C[16], *D[16];
+  bool peers_on = false;
+};
+static Multi2d g_m2;
+static std::mutex g_m2_mu;
+
+static void multi2d_free() {
+  for (int g = 0; g < g_m2.G; ++g) {
+    cudaSetDevice(g);
+    cudaFree(g_m2.C[g]);
+    cudaFree(g_m2.D[g]);
+    cudaStreamDestroy(g_m2.st[g]);
+    cudaEventDestroy(g_m2.ev[g]);
+  }
+  g_m2.G = g_m2.l = g_m2.m = 0;
+  cudaSetDevice(0);
+}
+
+static bool multi2d_prepare(int l, int m, int G) {
+  if (g_m2.l == l && g_m2.m == m && g_m2.G == G) return true;
+  if (g_m2.G) multi2d_free();
+  if (!g_m2.peers_on) {
+    for (int a = 0; a < G; ++a)
+      for (int b = 0; b < G; ++b) {
+        if (a == b) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can) {
+          set_error("devices %d and %d cannot access each other's memory", a, b);
+          return false;
+        }
+        cudaSetDevice(a);
+        cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_ok(e, "cudaDeviceEnablePeerAccess");
+        cudaGetLastError();
+      }
+    g_m2.peers_on = true;
+  }
+  const size_t slab = (size_t)l * m / G * 16;
+  bool ok = true;
+  for (int g = 0; g < G && ok; ++g) {
+    cudaSetDevice(g);
+    ok = cuda_ok(cudaMalloc(&g_m2.C[g], slab), "cudaMalloc(slab)") && cuda_ok(cudaMalloc(&g_m2.D[g], slab), "cudaMalloc(slab)") &&
+         cuda_ok(cudaStreamCreateWithFlags(&g_m2.st[g], cudaStreamNonBlocking), "cudaStreamCreate") &&
+         cuda_ok(cudaEventCreateWithFlags(&g_m2.ev[g], cudaEventDisableTiming), "cudaEventCreate");
+    if (ok) g_m2.G = g + 1;
+  }
+  cudaSetDevice(0);
+  if (!ok) {
+    multi2d_free();
+    return false;
+  }
+  g_m2.l = l;
+  g_m2.m = m;
+  return true;
+}
+
+static bool multi2d_eligible(int ldim, int l, int m, void *c) {
+  const int G = devices_in_use();
+  if (G < 2 || G > 16 || (G & (G - 1)) || ldim != l) return false;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != 0) return false;
+  auto pow2_in_range = [](int v) { return v >= 4096 && v <= (1 << 20) && (v & (v - 1)) == 0; };
+  if (!pow2_in_range(l) || !pow2_in_range(m) || l % G || m % G) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, c) != cudaSuccess) {
+    cudaGetLastError();
+    return true;  // unregistered host memory
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeUnregistered;
+}
+
+static bool complex_2d_multi(int l, int m, void *c, int dir) {
+  std::lock_guard<std::mutex> lk(g_m2_mu);
+  const int G = devices_in_use();
+  if (!multi2d_prepare(l, m, G)) return false;
+  const size_t slab = (size_t)l * m / G * 16;
+  cudaStream_t saved = t_stream;
+  bool ok = true;
+  auto barrier = [&]() {  // every device's stream waits for all the others
+    for (int g = 0; g < G && ok; ++g) {
+      cudaSetDevice(g);
+      ok = cuda_ok(cudaEventRecord(g_m2.ev[g], g_m2.st[g]), "cudaEventRecord");
+    }
+    for (int g = 0; g < G && ok; ++g) {
+      cudaSetDevice(g);
+      for (int h = 0; h < G && ok; ++h)
+        if (h != g) ok = cuda_ok(cudaStreamWaitEvent(g_m2.st[g], g_m2.ev[h], 0), "cudaStreamWaitEvent");
+    }
+  };
+  for (int g = 0; g < G && ok; ++g) {
+    cudaSetDevice(g);
+    ok = cuda_ok(cudaMemcpyAsync(g_m2.C[g], (char *)c + (size_t)g * slab, slab, cudaMemcpyHostToDevice, g_m2.st[g]), "cudaMemcpyAsync(H2D slab)");
+  }
+  for (int phase = 1; phase <= 2 && ok; ++phase) {
+    barrier();  // phase 1: all slabs are in place (a peer's D must not be written while ... it is free here); phase 2: all D complete
+    for (int g = 0; g < G && ok; ++g) {
+      cudaSetDevice(g);
+      t_stream = g_m2.st[g];
+      ok = run_c2c_2d_sharded_phase(phase, dir, l, m, g, G, phase == 1 ? g_m2.C[g] : g_m2.D[g], phase == 1 ? g_m2.D : g_m2.C);
+    }
+  }
+  barrier();  // all column slabs complete
+  for (int g = 0; g < G && ok; ++g) {
+    cudaSetDevice(g);
+    ok = cuda_ok(cudaMemcpyAsync((char *)c + (size_t)g * slab, g_m2.C[g], slab, cudaMemcpyDeviceToHost, g_m2.st[g]), "cudaMemcpyAsync(D2H slab)");
+  }
+  for (int g = 0; g < G; ++g) {
+    cudaSetDevice(g);
+    ok = cuda_ok(cudaStreamSynchronize(g_m2.st[g]), "cudaStreamSynchronize") && ok;
+  }
+  cudaSetDevice(0);
+  t_stream = saved;
+  return ok;
+}
+static void multi2d_release() {
+  std::lock_guard<std::mutex> lk(g_m2_mu);
+  if (g_m2.G) multi2d_free();
+}
+#endif
+
 static int complex_2d(int *ldim, int *l, int *m, void *c, int *lensav, int *lenwrk, int *ier, int dir) {
   *ier = 0;
   if (*l < 1 || *m < 1) return 0;
@@ -503,6 +638,10 @@ static int complex_2d(int *ldim, int *l, int *m, void *c, int *lensav, int *lenw
   else if (*lensav < 2 * *l + log2_floor_ref(*l) + 2 * *m + log2_floor_ref(*m) + 8) *ier = 2;
   else if ((long long)*lenwrk < 2LL * *l * *m) *ier = 3;
   if (*ier) return 0;
+  if (device_ready() && multi2d_eligible(*ldim, *l, *m, c)) {
+    if (!complex_2d_multi(*l, *m, c, dir)) *ier = -1;
+    return 0;
+  }
   DeviceView v;
   bool ok = view_open(c, ((size_t)*ldim * (*m - 1) + *l) * 16, v);
   if (ok) ok = run_c2c_2d(*ldim, *l, *m, dir, v.dev);
@@ -778,6 +917,7 @@ int cfb200_synchronize(void) {
 unsigned long long cfb200_launch_count(void) { return launch_count(); }
 const char *cfb200_last_error(void) { return last_error(); }
 void cfb200_release(void) {
+  multi2d_release();
   release_plans();
   scratch_release_all();
   if (t_bounce.p) {

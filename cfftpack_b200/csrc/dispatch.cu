@@ -216,12 +216,18 @@ struct OverlapStreams {
   int dev = -1;
   bool ok = false;
 };
-static thread_local OverlapStreams t_ov;
+static thread_local OverlapStreams t_ov_all[16];  // per device: one host thread may drive several GPUs (cfft2f_ fan-out)
+#define t_ov (t_ov_all[ov_dev_index()])
+static int ov_dev_index() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < 16 ? dev : 0;
+}
 static bool overlap_ready() {
   int dev = 0;
   cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return false;
   if (t_ov.ok && t_ov.dev == dev) return true;
-  if (t_ov.ok) return false;  // one device per host thread for this path
   for (auto &s : t_ov.st) CFB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   CFB_CUDA(cudaEventCreateWithFlags(&t_ov.ev_start, cudaEventDisableTiming));
   for (auto &e : t_ov.ev1) CFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

@@ -686,6 +686,22 @@ for fam, n, lot in (("cfft", 4096, 3001), ("rfft", 4096, 5000), ("cosq", 1001, 4
         want, ier = ORC.run1(fam, "f", n, a)
         if fl.rel_l2(b, want) > fl.tol(n):
             bad += 1; print("MISMATCH", fam, n, lot, r, fl.rel_l2(b, want))
+# cfft2f_ on a host matrix: one GPU vs two (column slabs + fused P2P transposes inside the library)
+l = 4096
+h = torch.empty(l * l * 2, dtype=torch.float64, pin_memory=True).uniform_(-1, 1)
+P = fl.Lib(fl.product())
+outs = []
+for ndev in (1, 2):
+    assert cb.lib.cfb200_set_devices(ndev) == ndev
+    y, ier = P.run2("f", l, l, l, h.numpy().view(np.complex128))
+    assert ier == 0, cb.last_error()
+    outs.append(y)
+e2 = fl.rel_l2(outs[1], outs[0])
+if e2 > fl.tol(l * l):
+    bad += 1; print("MISMATCH cfft2 multi-GPU", e2)
+yb, ier = P.run2("b", l, l, l, outs[1])
+if ier != 0 or fl.rel_l2(yb, h.numpy().view(np.complex128)) > fl.tol(l * l):
+    bad += 1; print("MISMATCH cfft2 multi-GPU round trip", ier)
 print("BAD", bad)
 sys.exit(1 if bad else 0)
 """ % (fl.ROOT, fl.ROOT + "/tests")
