@@ -124,7 +124,7 @@ bool make_tensor_map3(TensorMap3 *tm, const void *base, unsigned long long d0, u
 }
 
 static thread_local int t_tile_cap = 0;
-void set_tile_cta_cap(int per_sm) { t_tile_cap = per_sm; }
+void set_tile_cta_cap(int ctas) { t_tile_cap = ctas; }
 int tile_cta_cap() { return t_tile_cap; }
 
 int sm_count() {  // of the calling thread's current device

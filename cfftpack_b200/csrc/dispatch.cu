@@ -249,7 +249,13 @@ static bool run_c2c_pow2_four_step_pipelined(int n, int a1, int a2, long long lo
   if (!scr || !get_root_plan(n)) return false;
   bool ok = cuda_ok(cudaEventRecord(t_ov.ev_start, user), "cudaEventRecord");
   for (int k = 0; k < 2 && ok; ++k) ok = cuda_ok(cudaStreamWaitEvent(t_ov.st[k], t_ov.ev_start, 0), "cudaStreamWaitEvent");
-  set_tile_cta_cap(1);
+  // the two sweeps share the 2 CTA slots per SM: `split` eighths of them go to sweep 1 (HBM bound, quick), the rest to
+  // sweep 2 (NVLink bound).  CFB200_P2P_SPLIT=1..7, default 4 (one slot per SM each).
+  static const int split = [] {
+    const int v = getenv("CFB200_P2P_SPLIT") ? atoi(getenv("CFB200_P2P_SPLIT")) : 4;
+    return v >= 1 && v <= 7 ? v : 4;
+  }();
+  const int slots = 2 * sm_count(), cap1 = slots * split / 8, cap2 = slots - cap1;
   for (int ch = 0; ch < nch && ok; ++ch) {
     const long long m0 = (long long)ch * per, lc = lot - m0 < per ? lot - m0 : per;
     PeerOut sub = *po;
@@ -263,11 +269,13 @@ static bool run_c2c_pow2_four_step_pipelined(int n, int a1, int a2, long long lo
     cpx *buf = scr + (size_t)(ch & 1) * per * n;
     // sweep 1 (HBM bound) on stream 0; its buffer was last read by sweep 2 of chunk ch - 2
     set_current_stream(t_ov.st[0]);
+    set_tile_cta_cap(cap1);
     if (ch >= 2) ok = cuda_ok(cudaStreamWaitEvent(t_ov.st[0], t_ov.ev2[ch - 2], 0), "cudaStreamWaitEvent");
     ok = ok && run_c2c_pow2_four_step_chunk(n, a1, a2, lc, io, dir, scale, &sub, tw2 ? &t2 : nullptr, 1, buf) &&
          cuda_ok(cudaEventRecord(t_ov.ev1[ch], t_ov.st[0]), "cudaEventRecord");
     // sweep 2 (NVLink bound) on stream 1
     set_current_stream(t_ov.st[1]);
+    set_tile_cta_cap(cap2);
     ok = ok && cuda_ok(cudaStreamWaitEvent(t_ov.st[1], t_ov.ev1[ch], 0), "cudaStreamWaitEvent") &&
          run_c2c_pow2_four_step_chunk(n, a1, a2, lc, io, dir, scale, &sub, tw2 ? &t2 : nullptr, 2, buf) &&
          cuda_ok(cudaEventRecord(t_ov.ev2[ch], t_ov.st[1]), "cudaEventRecord");

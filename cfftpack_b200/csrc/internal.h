@@ -24,9 +24,9 @@ bool kernel_attrs_ready(const void *kernel, size_t smem);
 /* true once a CUDA device is usable; otherwise prints one loud line to stderr (there is no CPU path) */
 bool device_ready();
 int sm_count();
-/* cap on resident CTAs per SM for the tile kernels launched by the calling thread (0 = none): lets two persistent sweeps
- * of a pipelined sharded transform share the SMs */
-void set_tile_cta_cap(int per_sm);
+/* cap on the grid (CTAs) of the tile kernels launched by the calling thread (0 = none): lets the two persistent sweeps
+ * of a pipelined sharded transform share the SMs' CTA slots */
+void set_tile_cta_cap(int ctas);
 int tile_cta_cap();
 /* device copy of a host table, complete (not merely staged) on return; nullptr + last_error on failure */
 void *upload_table(const void *host, size_t bytes);

@@ -166,9 +166,9 @@ bool launch_tile_stream(TileParams &P) {
   const long long ntiles = (P.lot + C::TPB - 1) / C::TPB;
   long long per_sm = (long long)((SMEM_LIMIT + 1024) / (smem + 1024));
   if (per_sm > (C::THREADS > 256 ? 1 : 2)) per_sm = (C::THREADS > 256 ? 1 : 2);
-  if (tile_cta_cap() > 0 && per_sm > tile_cta_cap()) per_sm = tile_cta_cap();
   if (per_sm < 1) per_sm = 1;
   long long grid = per_sm * sm_count();
+  if (tile_cta_cap() > 0 && grid > tile_cta_cap()) grid = tile_cta_cap();  // share of the CTA slots (pipelined sweeps)
   if (grid > ntiles) grid = ntiles;
   CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, smem, current_stream(), P, ntiles);
   count_launch();
@@ -197,9 +197,9 @@ bool launch_tile_tma(TileParams &P, bool *declined) {  // *declined: the tensor 
   long long per_sm = (long long)((SMEM_LIMIT + 1024) / (smem + 1024));
   const long long reg_cap = C::THREADS <= 128 ? 4 : 2;
   if (per_sm > reg_cap) per_sm = reg_cap;
-  if (tile_cta_cap() > 0 && per_sm > tile_cta_cap()) per_sm = tile_cta_cap();
   if (per_sm < 1) per_sm = 1;
   long long grid = per_sm * sm_count();
+  if (tile_cta_cap() > 0 && grid > tile_cta_cap()) grid = tile_cta_cap();  // share of the CTA slots (pipelined sweeps)
   if (grid > ntiles) grid = ntiles;
   CFB_LAUNCH(kern, (unsigned)grid, C::THREADS, smem, current_stream(), P, tm, ntiles);
   count_launch();
