@@ -299,3 +299,71 @@ def test_randomized_shapes_small(libs):
             inc = int(rng.integers(2, 5))
             jump = inc * (n - 1) + 1 + int(rng.integers(0, 7))
         _check(S, O, fam, "fb"[int(rng.integers(2))], lot, jump, n, inc, seed=case)
+
+
+def _device_array(lib, count):
+    """16-byte aligned complex128 array registered as device memory with the emulator"""
+    import ctypes
+    lib.cfb200_sim_mark_device.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    buf = np.zeros(2 * count + 2)
+    off = (16 - buf.ctypes.data % 16) % 16 // 8
+    a = buf[off:off + 2 * count].view(np.complex128)
+    lib.cfb200_sim_mark_device(ctypes.c_void_p(a.ctypes.data), a.nbytes)
+    return a, buf
+
+
+def test_sharded_phases_two_ranks_emulated_in_one_process(libs):
+    """The multi-GPU phase entry points with G = 2 "ranks" run one after the other in this process: every
+    rank's slabs are ordinary arrays, the peer pointers point at the other rank's arrays, and a barrier is simply the end
+    of the loop over ranks.  Checks the slab/peer index arithmetic of the fused transposes, the W_N^(i b) twiddles and the
+    natural-order scatter of the long 1-D transform against the oracle -- no GPU, no NCCL."""
+    import ctypes
+    S, O = libs
+    lib = S.lib
+    I, G = ctypes.c_int, 2
+
+    def phase(fn, *args):
+        ier = I(-1)
+        fn(*args, ctypes.byref(ier))
+        assert ier.value == 0, lib.cfb200_last_error()
+
+    # ---- 2^24-point transform in natural order over two ranks: X = data chunks, Y = second buffer (result)
+    a = 24
+    n = 1 << a
+    x = fl.rand_input("cfft", n, 99)
+    X, Y, keep = [], [], []
+    for r in range(G):
+        xa, kb = _device_array(lib, n // G); keep.append(kb)
+        ya, kb = _device_array(lib, n // G); keep.append(kb)
+        xa[:] = x[r * (n // G):(r + 1) * (n // G)]
+        X.append(xa); Y.append(ya)
+    px = (ctypes.c_void_p * G)(*[v.ctypes.data for v in X])
+    py = (ctypes.c_void_p * G)(*[v.ctypes.data for v in Y])
+    f1 = lib.cfb200_cfft1_sharded_phase
+    for ph, src, dst in ((0, X, py), (1, Y, px), (2, X, py)):
+        for r in range(G):  # "barrier" = all ranks finish the phase before the next one starts
+            phase(f1, I(ph), I(-1), I(a), I(r), I(G), ctypes.c_void_p(src[r].ctypes.data), dst)
+    want, ier = O.run1("cfft", "f", n, x)
+    got = np.concatenate(Y)
+    assert fl.rel_l2(got, want) <= fl.tol(n)
+
+    # ---- 4096 x 4096 cfft2f on column slabs C[m_loc][l], row slabs D[m][l_loc] (another minute of emulation: opt-in;
+    # the same phases run on real GPUs in bench.py's `cfft2` object and in the 2-GPU tests)
+    if os.environ.get("CFB200_SLOW_TESTS") != "1":
+        return
+    l = m = 4096
+    c = fl.rand_input("cfft", l * m, 7)
+    C, D = [], []
+    for r in range(G):
+        ca, kb = _device_array(lib, l * m // G); keep.append(kb)
+        da, kb = _device_array(lib, l * m // G); keep.append(kb)
+        ca[:] = c[r * (l * m // G):(r + 1) * (l * m // G)]
+        C.append(ca); D.append(da)
+    pc = (ctypes.c_void_p * G)(*[v.ctypes.data for v in C])
+    pd = (ctypes.c_void_p * G)(*[v.ctypes.data for v in D])
+    f2 = lib.cfb200_cfft2_sharded_phase
+    for ph, src, dst in ((1, C, pd), (2, D, pc)):
+        for r in range(G):
+            phase(f2, I(ph), I(-1), I(l), I(m), I(r), I(G), ctypes.c_void_p(src[r].ctypes.data), dst)
+    want2, ier = O.run2("f", l, l, m, c)
+    assert fl.rel_l2(np.concatenate(C), want2) <= fl.tol(l * m)
