@@ -335,10 +335,16 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_stream_kernel(cpx *
     cpx a[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) a[i] = land[(size_t)tl * N + t + NT * i];
-    landing_reads_done(a, (volatile unsigned *)(bar + 1));
-    __syncthreads();  // the landing buffer has been consumed: refill it with the next tile while we compute
+    landing_reads_done<P, true>(a, (volatile unsigned *)(bar + 1));
+    // the landing buffer has been consumed: warp 0 waits for everybody's report and refills it with the next tile while
+    // the other warps are already computing
     const long long next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
+    if (tid < 32) {
+      named_sync(1, C::THREADS);
+      if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
+    } else {
+      named_arrive(1, C::THREADS);
+    }
     pow2_core_split<C, DIR>(a, xch + (size_t)tl * S::XTILE, t, tws);
     if (live) {
       cpx *x = c + g * jump + t;
@@ -400,10 +406,17 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
       }
     }
     landing_reads_done(a, (volatile unsigned *)(bar + 1));
-    if (BULK && t == 0) bulk_wait_read();  // the previous tile's rows have left the exchange tile
-    __syncthreads();
     const long long next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
+    if (BULK) {  // full barrier: the previous tile's rows must also have left the exchange tile before anybody writes it
+      if (t == 0) bulk_wait_read();
+      __syncthreads();
+      if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
+    } else if (tid < 32) {
+      named_sync(1, C::THREADS);
+      if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
+    } else {
+      named_arrive(1, C::THREADS);
+    }
     pow2_core_split<C, DIR>(a, xq, t, tws);
     if (DIR < 0) {
       // separate X_a, X_b: Z[N-f] of the upper half goes through the exchange tile, viewed as N/2 complex slots
@@ -817,8 +830,8 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS <= 128 ? 4 : 2)) pow2_
     cpx a[PP];
 #pragma unroll
     for (int i = 0; i < PP; ++i) a[i] = STAGED ? land[(size_t)tl * TS::LPITCH + t + NT * i] : land[(size_t)(t + NT * i) * TPB + tl];
-    landing_reads_done(a, (volatile unsigned *)(bar + 1));
-    __syncthreads();  // landing buffer consumed: refill it while we compute
+    landing_reads_done<PP, true>(a, (volatile unsigned *)(bar + 1));
+    __syncthreads();  // landing buffer consumed: refill it while we compute (split barrier: no gain here)
     const long long next = tile + gridDim.x;
     if (tid < 32 && next < ntiles) issue(next);
     pow2_core_split<C, DIR, false>(a, xr, t, tws);

@@ -163,9 +163,9 @@ __global__ void __launch_bounds__(R10Cfg<K>::THREADS, R10Cfg<K>::MINB) r10_c2c_s
     cpx a[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) a[i] = act ? land[(size_t)tl * N + t + NT * i] : make_double2(0.0, 0.0);
-    landing_reads_done(a, (volatile unsigned *)(bar + 1));
-    __syncthreads();
+    landing_reads_done<P, true>(a, (volatile unsigned *)(bar + 1));
     const long long next = tile + gridDim.x;
+    __syncthreads();  // (a split arrive/sync barrier, as in pow2_c2c_stream_kernel, measured slower here: 1.82 vs 1.68 ms)
     if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
     r10_core<C, K, DIR>(a, xch + (size_t)tl * C::XT, t, act, tws);
     if (live) {

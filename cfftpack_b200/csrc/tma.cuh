@@ -158,6 +158,21 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 #endif
 
+/* Split barrier (PTX bar.arrive / bar.sync on a named barrier): the warps that only have to REPORT that they are done
+ * with the landing buffer arrive and run on; only the warp that issues the next bulk copy waits.  Under the emulator
+ * both are a full barrier (its bulk copies complete at once, so nobody may run ahead). */
+#ifdef CFB_SIM
+__device__ __forceinline__ void named_arrive(int, int) { __syncthreads(); }
+__device__ __forceinline__ void named_sync(int, int) { __syncthreads(); }
+#else
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+#endif
+
 /* Handing a landing buffer back to the bulk-copy engine.  The engine writes shared memory through the async proxy and
  * may overtake ordinary shared-memory reads that are still queued in the SM's memory pipeline when the CTA passes the
  * barrier that precedes the next bulk copy (observed as rare corrupt tiles).  Every kernel therefore calls this before
@@ -165,12 +180,16 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
  * all of them feeds a (never taken, harmless) predicated shared-memory store, so the reads have delivered their values
  * before the barrier -- without the cost of fence.proxy.async, which also drains the previous tile's global stores
  * (measured: rfftmf 0.82 -> 0.88 ms with the fence).  `spare` is any 4-byte shared-memory word the kernel does not use. */
-template <int P>
+/* WHOLE: every a[i] was filled by ONE 16-byte load, so one of its four registers stands for the load */
+template <int P, bool WHOLE = false>
 __device__ __forceinline__ void landing_reads_done(const double2 (&a)[P], volatile unsigned *spare) {
 #ifndef CFB_SIM
   unsigned acc = 0;
 #pragma unroll
-  for (int i = 0; i < P; ++i) acc ^= (unsigned)__double2loint(a[i].x) ^ (unsigned)__double2hiint(a[i].y);
+  for (int i = 0; i < P; ++i) {
+    acc ^= (unsigned)__double2loint(a[i].x);
+    if (!WHOLE) acc ^= (unsigned)__double2hiint(a[i].y);
+  }
   if (acc == 0x9e3779b9u) *spare = acc;
 #endif
 }
