@@ -130,24 +130,31 @@ __device__ __forceinline__ void mix_pass_generic(cpx *__restrict__ src, cpx *__r
         br[b][u] = bi[b][u] = 0.0;
       }
     }
+    // root look-ups by BYTE offset (j k mod R) * 16 kept as a running sum: add, compare, conditional subtract per root
+    // (indexing rt[] with an element index cost two more integer instructions each: 79 integer vs 52 FP64 per two j)
+    const char *rtb = (const char *)rt;
+    constexpr unsigned LIM = R * (unsigned)sizeof(cpx);
 #pragma unroll
     for (int u = 0; u < KB; ++u) idx[u] = 0;
+    const cpx *pp = src + q, *mp = src + q + S * R;
 #pragma unroll 2
     for (int j = 1; j <= H; ++j) {
       cpx p[QB], m[QB];
+      pp += S;
+      mp -= S;
 #pragma unroll
       for (int b = 0; b < QB; ++b) {
-        p[b] = src[q + b + S * j];
-        m[b] = src[q + b + S * (R - j)];
+        p[b] = pp[b];
+        m[b] = mp[b];
         s0x[b] += p[b].x;
         s0y[b] += p[b].y;
       }
 #pragma unroll
       for (int u = 0; u < KB; ++u) {
-        int i2 = idx[u] + (k0 + u);  // (j k) mod R by a running sum (k0 + u < R)
-        i2 -= (i2 >= R) ? R : 0;
-        idx[u] = i2;
-        const cpx w = rt[i2];  // (cos, -sin)(2 pi j k / R)
+        unsigned i2 = (unsigned)idx[u] + (unsigned)(k0 + u) * (unsigned)sizeof(cpx);  // < 2 LIM
+        i2 -= (i2 >= LIM) ? LIM : 0u;
+        idx[u] = (int)i2;
+        const cpx w = *(const cpx *)(rtb + i2);  // (cos, -sin)(2 pi j k / R)
 #pragma unroll
         for (int b = 0; b < QB; ++b) {
           ar[b][u] = fma(w.x, p[b].x, ar[b][u]);
