@@ -493,9 +493,10 @@ for fam, n, lot in (("cfft", 16384, 96), ("cfft", 10007, 64), ("rfft", 32768, 96
         cb.synchronize()
         assert plan.multi("f", hh.data_ptr(), lot, n, 1, lot * n) == 0, cb.last_error()
         # complex: bit for bit.  Real families pair rows (z = x_a + i x_b) inside a chunk, so a chunk boundary at an odd
-        # row re-pairs them and moves the rounding by an ulp; a scratch race would be a gross error.
+        # row re-pairs them and moves the rounding (the running sums of cost/sint amplify it to ~1e-14 relative; the
+        # inputs are unseeded, so 1e-14 was borderline); a scratch race would be a gross error.
         ref_ = dd.cpu()
-        same = torch.equal(hh, ref_) if fam == "cfft" else float((hh - ref_).norm() / ref_.norm()) <= 1e-14
+        same = torch.equal(hh, ref_) if fam == "cfft" else float((hh - ref_).norm() / ref_.norm()) <= 2e-13
         if not same:
             bad += 1
             print("MISMATCH", fam, n, lot, rep, float((hh - ref_).abs().max()))
