@@ -217,12 +217,12 @@ struct OverlapStreams {
   bool ok = false;
 };
 static thread_local OverlapStreams t_ov_all[16];  // per device: one host thread may drive several GPUs (cfft2f_ fan-out)
-#define t_ov (t_ov_all[ov_dev_index()])
-static int ov_dev_index() {
+static OverlapStreams &ov_current() {  // the calling thread's set for its current device
   int dev = 0;
   cudaGetDevice(&dev);
-  return dev >= 0 && dev < 16 ? dev : 0;
+  return t_ov_all[dev >= 0 && dev < 16 ? dev : 0];
 }
+#define t_ov (ov_current())
 static bool overlap_ready() {
   int dev = 0;
   cudaGetDevice(&dev);

@@ -130,7 +130,8 @@ unsigned long long cfb200_launch_count(void);
 /* message of the last failure on this thread ("" if none) */
 const char *cfb200_last_error(void);
 /* free cached device plans (all threads) and the calling thread's scratch buffers.  The process must be quiescent: no
- * other host thread inside a transform; the call waits for the device to go idle first. */
+ * other host thread inside a transform; the call waits for the device to go idle first.  The worker threads of
+ * cfb200_set_devices keep their staging buffers until the process exits. */
 void cfb200_release(void);
 /* "cfftpack_b200 <version> sm_100a" */
 const char *cfb200_version(void);
