@@ -61,7 +61,7 @@ def hbm_peak():
 def workload_config(fam, n, lot):
     """identical for the b200 arm and the reference arm (the driver compares them)"""
     bytes_rank = algorithmic_bytes(fam, n, lot)
-    return {"workload": f"{fam}mf N={n} lot={lot} per GPU, inc=1, jump=N, in place, forward (BASELINE configs[1])",
+    return {"workload": f"{fam}mf N={n} lot={lot} per GPU, inc=1, jump=N, in place, forward (BASELINE configs[{1 if fam == 'cfft' else 2}])",
             "sharding": "by lot, one process per GPU, no collective",
             "l2": f"inputs {bytes_rank // 2 >> 20} MiB per GPU >> 126 MB L2, no flush needed"}
 
