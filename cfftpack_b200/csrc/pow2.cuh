@@ -578,13 +578,12 @@ __device__ __forceinline__ void tile_store(const TileParams &P, cpx (&a)[C::P], 
     const int j = (int)(P.fs_from_hi ? hi : lo);
     const int mask = (1 << P.fs_shift) - 1, sh = P.fs_shift, nmask = P.fs_nmask;
     auto root = [&](int x) { return cmul(fss[x & mask], fss[mask + 1 + (x >> sh)]); };
+    // a[i] *= b0 w1^i in place: a table of the 16 products would cost 64 registers (it spilled: the sweeps' top stall
+    // was long_scoreboard on local memory)
     const cpx b0 = root(j * t), w1 = root((j * NT) & nmask), w4 = root((4 * j * NT) & nmask);
-    cpx b[PP];
 #pragma unroll
-    for (int i = 0; i < PP; ++i) b[i] = b0;
-    twiddle_powers<-1>(b, w1, w4);  // b[i] = b0 * w1^i
-#pragma unroll
-    for (int i = 0; i < PP; ++i) a[i] = ctw<DIR>(a[i], b[i]);
+    for (int i = 0; i < PP; ++i) a[i] = ctw<DIR>(a[i], b0);
+    twiddle_powers<DIR>(a, w1, w4);
   }
   if (P.tw2) {
     const int seq_lo = P.tw2_seq_lo;
@@ -595,12 +594,9 @@ __device__ __forceinline__ void tile_store(const TileParams &P, cpx (&a)[C::P], 
     const cpx *tb = P.tw2;
     auto root = [&](long long x) { return cmul(__ldg(tb + (x & lmask)), __ldg(tb + lmask + 1 + (x >> sh))); };
     const cpx b0 = root((seq * k0 + step * t) & mask), w1 = root((step * NT) & mask), w4 = root((4 * step * NT) & mask);
-    cpx b[PP];
 #pragma unroll
-    for (int i = 0; i < PP; ++i) b[i] = b0;
-    twiddle_powers<-1>(b, w1, w4);
-#pragma unroll
-    for (int i = 0; i < PP; ++i) a[i] = ctw<DIR>(a[i], b[i]);
+    for (int i = 0; i < PP; ++i) a[i] = ctw<DIR>(a[i], b0);
+    twiddle_powers<DIR>(a, w1, w4);
   }
   if (P.npeers > 0) {
     // fused transpose: each element is stored straight into the memory of the GPU that owns its slab
