@@ -368,7 +368,10 @@ static bool run_on_array(void *user, size_t esz, long long lot, long long jump, 
   cudaGetDevice(&cur);
   if (G <= 1 || cur != 0 || lot < 2 * G || jump < seq_span)
     return run_on_array_one(user, esz, lot, jump, n, inc, fn, (int)at.type);
-  // fan out: shard g = sequences [lot g / G, lot (g+1) / G)
+  // fan out: shard g = sequences [lot g / G, lot (g+1) / G).  One fan-out at a time per process: the workers have one
+  // job slot each (concurrent callers queue up here; their transfers would share the same PCIe links anyway)
+  static std::mutex fan_mu;
+  std::lock_guard<std::mutex> fan_lock(fan_mu);
   g_pool.ensure(G - 1);
   {
     std::lock_guard<std::mutex> lk(g_pool.mu);
