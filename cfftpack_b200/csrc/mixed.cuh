@@ -243,6 +243,11 @@ __global__ void __launch_bounds__(W, (W <= 96 ? 4 : W <= 128 ? 3 : 2)) mix_strea
   for (; tile < npairs; tile += gridDim.x) {
     mbar_wait(bar, parity);
     parity ^= 1;
+    if constexpr (C::R1 == 1) {
+      // two-pass lengths: pass 0 writes Q, which the previous pair's bulk store may still be reading
+      if (t == 0) bulk_wait_read();
+      __syncthreads();
+    }
     /* ---- pass 0 (radix R0): the family's pre-processing happens in the loader ---- */
     double dsa = 0.0, dsb = 0.0;                     // cost: this thread's share of dsum (costf1_ :6361-6371)
     const double ends = (KIND == K_COST && DIR > 0) ? 2.0 : 1.0;  // costb1_ doubles the end points first
