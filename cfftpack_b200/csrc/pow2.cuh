@@ -786,7 +786,14 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS <= 128 ? 4 : 2)) pow2_
   typedef TileTmaSmem<C, STAGED> TS;
   typedef StreamSmem<C> S;
   constexpr int PP = C::P, NT = C::NT, TPB = C::TPB, N = C::N;
-  char *base = (char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);  // the tensor box must land 128-byte aligned
+  // the tensor box must land 128-byte aligned.  The offset is added to the shared array itself: rounding the pointer
+  // through an integer made the compiler lose the address space, and every exchange access became a generic LD/ST
+  // (the sweeps' top stalls were lg_throttle / long_scoreboard, profiles/r2_ncu_tile_cfft2.txt)
+#ifdef CFB_SIM
+  char *base = (char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+#else
+  char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+#endif
   cpx *land = (cpx *)base;
   double *xch = (double *)(base + TS::LAND);
   cpx *tws = (cpx *)(base + TS::LAND + TS::XCH);
