@@ -931,9 +931,9 @@ void cfb200_release(void) {
 }
 const char *cfb200_version(void) {
 #ifdef CFB_SIM
-  return "cfftpack_b200 0.1 SIM (CPU thread emulator, tests only)";
+  return "cfftpack_b200 0.2 SIM (CPU thread emulator, tests only)";
 #else
-  return "cfftpack_b200 0.1 sm_100a";
+  return "cfftpack_b200 0.2 sm_100a";
 #endif
 }
 int cfb200_max_onchip_complex(void) { return engine_max_c2c(); }
