@@ -300,13 +300,17 @@ __device__ __forceinline__ void pow2_core_split(cpx (&a)[C::P], double *__restri
 }
 
 /* thread 0: arm the barrier and start the bulk copies of one tile (TPB sequences of `bytes` each) */
-template <int TPB>
+template <int TPB, bool L2_AHEAD = false>
 __device__ __forceinline__ void stream_issue(char *land, const char *gbase, long long lot, long long jump_bytes,
                                              long long tile, unsigned seq_bytes, uint64_t *bar) {
   const long long g0 = tile * TPB;
   const int live = (int)((lot - g0) < TPB ? (lot - g0) : TPB);
   mbar_expect_tx(bar, (unsigned)live * seq_bytes);
   for (int i = 0; i < live; ++i) bulk_g2s(land + (size_t)i * seq_bytes, gbase + (g0 + i) * jump_bytes, seq_bytes, bar);
+  if (L2_AHEAD) {  // also pull the tile after this one into L2 (measured: real kernel +1.6 %, complex kernel -15 %)
+    const long long g2 = (tile + gridDim.x) * TPB;
+    for (int i = 0; i < TPB && g2 + i < lot; ++i) bulk_prefetch_l2(gbase + (g2 + i) * jump_bytes, seq_bytes);
+  }
 }
 
 template <class C, int MINB, int DIR>
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
   // a tile = TPB pairs = 2*TPB consecutive sequences; reuse stream_issue with a "sequence" = one real row
   constexpr int ROWS = 2 * C::TPB;
   long long tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, tile, N * 8, bar);
+  if (tid == 0 && tile < ntiles) stream_issue<ROWS, true>((char *)land, (const char *)r, lot, jump * 8, tile, N * 8, bar);
   unsigned parity = 0;
   const double *la = land + (size_t)(2 * tl) * N, *lb = la + N;
   double *xq = xch + (size_t)tl * S::XTILE;
@@ -410,10 +414,10 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_r2c_stream_kernel(doubl
     if (BULK) {  // full barrier: the previous tile's rows must also have left the exchange tile before anybody writes it
       if (t == 0) bulk_wait_read();
       __syncthreads();
-      if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
+      if (tid == 0 && next < ntiles) stream_issue<ROWS, true>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
     } else if (tid < 32) {
       named_sync(1, C::THREADS);
-      if (tid == 0 && next < ntiles) stream_issue<ROWS>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
+      if (tid == 0 && next < ntiles) stream_issue<ROWS, true>((char *)land, (const char *)r, lot, jump * 8, next, N * 8, bar);
     } else {
       named_arrive(1, C::THREADS);
     }

@@ -48,6 +48,7 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
 __device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
   bulk_g2s(smem_dst, gsrc, bytes, bar);
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *, unsigned) {}  // L2 prefetch: nothing to emulate
 /* shared -> global bulk store (emulated: an immediate copy, so the group waits are no-ops) */
 __device__ __forceinline__ void fence_async_smem() {}
 __device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, unsigned bytes) {
@@ -143,6 +144,9 @@ __device__ __forceinline__ void bulk_g2s_stream(void *smem_dst, const void *gsrc
           smem_u32(smem_dst)),
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gsrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 /* ---- shared -> global bulk stores (SASS UBLKCP.G.S): one instruction drains a finished row from shared memory ----
  * every thread that wrote the source executes fence_async_smem() before the barrier that precedes the store */
