@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_stream_kernel(cpx *
   for (int i = tid; i < S::TWS_COUNT; i += C::THREADS) tws[i] = __ldg(tw + i);
   __syncthreads();
   long long tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, tile, N * 16, bar);
+  if (tid == 0 && tile < ntiles) stream_issue<C::TPB, (C::N >= 8192)>((char *)land, (const char *)c, lot, jump * 16, tile, N * 16, bar);
   unsigned parity = 0;
   for (; tile < ntiles; tile += gridDim.x) {
     mbar_wait(bar, parity);
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(C::THREADS, MINB) pow2_c2c_stream_kernel(cpx *
     const long long next = tile + gridDim.x;
     if (tid < 32) {
       named_sync(1, C::THREADS);
-      if (tid == 0 && next < ntiles) stream_issue<C::TPB>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
+      if (tid == 0 && next < ntiles) stream_issue<C::TPB, (C::N >= 8192)>((char *)land, (const char *)c, lot, jump * 16, next, N * 16, bar);
     } else {
       named_arrive(1, C::THREADS);
     }
